@@ -1,0 +1,191 @@
+/*
+ * a1mpc.h -- C ABI of the B200-native batched convex-MPC QP engine.
+ *
+ * Drop-in boundary for the hot path of ShuoYangRobotics/A1-QP-MPC-Controller:
+ *   ConvexMpc            (src/a1_cpp/src/ConvexMpc.h:22-94,  ConvexMpc.cpp:7-260)
+ *   A1RobotControl::compute_grf, MPC branch (src/a1_cpp/src/A1RobotControl.cpp:446-562)
+ *   A1RobotControl::compute_grf, QP  branch (src/a1_cpp/src/A1RobotControl.cpp:377-445)
+ *   OsqpEigen::Solver set-up / solve / getSolution call sites
+ *                        (A1RobotControl.cpp:416-439, 522-555; test/test_mpc.cpp:131-151)
+ *
+ * Plain C, no Eigen / STL / torch types.  Every function returns 0 on success and a negative
+ * A1MPC_E* code on failure; a1mpc_last_error() gives the message of the calling thread's last
+ * failure.  A handle owns one CUDA device + one stream + scratch; it is NOT thread-safe,
+ * distinct handles are independent.  There is no CPU fallback: without a usable CUDA device
+ * a1mpc_create() fails with A1MPC_ENODEVICE.
+ *
+ * Batch layout: every per-QP field is batch-major SoA ("field-major, QP index fastest"):
+ * element (field f, QP b) of an array documented as [F][B] lives at  base[f * ld + b]  where
+ * ld is the `ld` member of the struct (ld >= B; ld == B for a dense batch).  This is what makes
+ * a warp's loads coalesced on the device.
+ */
+#ifndef A1MPC_H_
+#define A1MPC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define A1MPC_VERSION 100
+
+/* error codes */
+#define A1MPC_OK          0
+#define A1MPC_EINVAL     -1   /* bad argument / unsupported configuration            */
+#define A1MPC_ENODEVICE  -2   /* no usable CUDA device (there is no CPU fallback)    */
+#define A1MPC_ECUDA      -3   /* CUDA runtime error, see a1mpc_last_error()          */
+#define A1MPC_ENOMEM     -4
+#define A1MPC_ENCCL      -5   /* NCCL not loadable / NCCL error                      */
+
+/* per-QP status written by the solve kernels */
+#define A1MPC_STATUS_OPTIMAL     0  /* KKT certificate verified in-kernel (exact active set)  */
+#define A1MPC_STATUS_IPM_ONLY    1  /* interior-point iterate returned, finisher not verified */
+#define A1MPC_STATUS_MAXITER     2  /* iteration cap hit before the IPM tolerance             */
+#define A1MPC_STATUS_NUMERICAL   3  /* non-positive pivot / NaN in the inputs                 */
+#define A1MPC_STATUS_NO_CONTACT  4  /* no stance foot: all forces are zero by the constraints */
+
+#define A1MPC_MAX_HORIZON 20
+
+typedef struct a1mpc_handle a1mpc_handle;
+
+/* Batch-uniform configuration; mirrors the constants of the reference.
+ *   horizon          PLAN_HORIZON                      (A1Params.h:26)            10 | 20
+ *   dt               mpc_dt                            (A1RobotControl.cpp:462)
+ *   mu,fz_min,fz_max friction pyramid and fz bounds    (ConvexMpc.cpp:8, 223-224)
+ *   mass, inertia    robot_mass, a1_trunk_inertia      (A1CtrlStates.h:40-43), row-major
+ *   q[13], r[12]     q_weights, r_weights (un-doubled; the engine applies the factor 2 of
+ *                    ConvexMpc.cpp:20,41)
+ *   max_iter, tol    solver controls; 0 selects the defaults (40, 1e-9 switch-over mu)
+ */
+typedef struct a1mpc_config {
+  int    horizon;
+  int    precision;      /* 64 (fp64 everywhere).  32 is reserved  */
+  double dt;
+  double mu, fz_min, fz_max;
+  double mass;
+  double inertia[9];
+  double q[13];
+  double r[12];
+  int    max_iter;
+  double tol;
+} a1mpc_config;
+
+/* Fills cfg with the reference launch defaults (config/gazebo_a1_mpc.yaml:6-72,
+ * a1_ctrl.launch:2-3): N=10, dt=0.0025, mu=0.3, fz in [0,180], mass 12, gazebo weights. */
+void a1mpc_default_config(a1mpc_config* cfg);
+
+/* Inputs of A1RobotControl::compute_grf's MPC branch, i.e. the A1CtrlStates fields it reads
+ * (A1RobotControl.cpp:452-488, 498-503; A1CtrlStates.h:347-413).  Pointers are ALL host or ALL
+ * device (detected with cudaPointerGetAttributes).
+ *   x0      [12][B]  root_euler(3), root_pos(3), root_ang_vel(3), root_lin_vel(3)  (world)
+ *   rot     [9][B]   root_rot_mat, row-major
+ *   foot    [12][B]  foot_pos_abs, leg-major: FL(x,y,z), FR, RL, RR  (A1CtrlStates.h:399)
+ *   ref     [9][B]   root_euler_d[0], root_euler_d[1], root_ang_vel_d(3), root_lin_vel_d(3, body),
+ *                    root_pos_d[2]
+ *   contact [B]      bit i set = state.contacts[i]   (leg order FL,FR,RL,RR)
+ */
+typedef struct a1mpc_inputs {
+  const double*   x0;
+  const double*   rot;
+  const double*   foot;
+  const double*   ref;
+  const uint32_t* contact;
+  size_t          ld;
+} a1mpc_inputs;
+
+/* Outputs.  f_body is what compute_grf returns (A1RobotControl.cpp:555-563): R^T * u[3i:3i+3],
+ * first horizon step, leg-major.  status is mandatory; iters and u_full may be NULL.
+ *   f_body [12][B]   status [B]   iters [B] (IPM iterations + 100*finisher rounds)
+ *   u_full [12*N][B] world-frame solution over the whole horizon (OsqpEigen getSolution()) */
+typedef struct a1mpc_outputs {
+  double*  f_body;
+  int32_t* status;
+  int32_t* iters;
+  double*  u_full;
+  size_t   ld;
+} a1mpc_outputs;
+
+/* ---- life cycle --------------------------------------------------------------------------- */
+int  a1mpc_create(a1mpc_handle** out, const a1mpc_config* cfg, int device);
+int  a1mpc_destroy(a1mpc_handle* h);
+const char* a1mpc_last_error(void);
+int  a1mpc_device_count(void);
+
+/* ---- the hot path: replaces compute_grf's MPC branch for B robots -------------------------- */
+/* One call = build (linearise, condense, Hessian, gradient) + QP solve + force extraction for
+ * every QP of the batch.  Host pointers: pinned-staged H2D, solve, D2H, synchronous.  Device
+ * pointers: enqueued on the handle's stream, asynchronous (use a1mpc_sync). */
+int  a1mpc_solve_batch(a1mpc_handle* h, int B, const a1mpc_inputs* in, const a1mpc_outputs* out);
+
+/* ---- ConvexMpc members, for parity with the reference class (ConvexMpc.h:87-93) ----------- */
+/* Dense QP data exactly as ConvexMpc::calculate_qp_mats leaves it after compute_grf drove it
+ * (constant B_d over the horizon, A1RobotControl.cpp:498-514).  QP-major outputs:
+ *   H [B][12N][12N] row-major (hessian, densified), g [B][12N] (gradient),
+ *   lb, ub [B][20N] (ConvexMpc.cpp:223-245; +-1e30 = OsqpEigen::INFTY).  Any may be NULL. */
+int  a1mpc_build_qp_batch(a1mpc_handle* h, int B, const a1mpc_inputs* in,
+                          double* H, double* g, double* lb, double* ub);
+
+/* ConvexMpc::calculate_qp_mats for caller-supplied discrete models (the public API allows a
+ * different B_d per step: test/test_mpc.cpp:106-122).  QP-major inputs:
+ *   A_d [B][13][13] row-major, B_d_list [B][13N][12] row-major (B_mat_d_list),
+ *   x0 [B][13] (mpc_states), x_d [B][13N] (mpc_states_d);  outputs as above. */
+int  a1mpc_qp_mats_batch(a1mpc_handle* h, int B, const double* A_d, const double* B_d_list,
+                         const double* x0, const double* x_d, double* H, double* g);
+
+/* OsqpEigen::Solver replacement for the MPC QP (A1RobotControl.cpp:522-555):
+ *   min 1/2 u'Hu + g'u  s.t. the friction pyramid of ConvexMpc.cpp:46-58 with the contact
+ *   pattern `contact` (constant over the horizon).  H [B][12N][12N], g [B][12N] QP-major,
+ *   u [B][12N] out (getSolution()), status [B]. */
+int  a1mpc_solve_dense_batch(a1mpc_handle* h, int B, const double* H, const double* g,
+                             const uint32_t* contact, double* u, int32_t* status);
+
+/* ---- compute_grf's QP branch (stance_leg_control_type == 0), A1RobotControl.cpp:377-445 ---- */
+/* 12-variable instantaneous GRF QP, batched.  All arrays QP-major:
+ *   root_acc [B][6]  desired wrench (A1RobotControl.cpp:379-391, caller-computed PD + gravity)
+ *   rot_z [B][9], rot [B][9]  root_rot_mat_z, root_rot_mat (row-major); foot [B][12] leg-major
+ *   contact [B];  f_body [B][12] out;  status [B] out.
+ * Constants Q=diag(1,1,1,400,400,100), R=1e-3, mu=0.7, F in [0,180] (A1RobotControl.cpp:11-15). */
+int  a1mpc_grf_qp_batch(a1mpc_handle* h, int B, const double* root_acc, const double* rot_z,
+                        const double* rot, const double* foot, const uint32_t* contact,
+                        double* f_body, int32_t* status);
+
+/* ---- device memory, stream and timing helpers (so hosts need no CUDA headers) -------------- */
+int  a1mpc_device_alloc(a1mpc_handle* h, size_t bytes, void** ptr);
+int  a1mpc_device_free(a1mpc_handle* h, void* ptr);
+int  a1mpc_host_alloc(a1mpc_handle* h, size_t bytes, void** ptr);   /* pinned */
+int  a1mpc_host_free(a1mpc_handle* h, void* ptr);
+int  a1mpc_memcpy_h2d(a1mpc_handle* h, void* dst, const void* src, size_t bytes);  /* async on the stream */
+int  a1mpc_memcpy_d2h(a1mpc_handle* h, void* dst, const void* src, size_t bytes);  /* async on the stream */
+int  a1mpc_sync(a1mpc_handle* h);
+int  a1mpc_event_create(a1mpc_handle* h, void** ev);
+int  a1mpc_event_destroy(a1mpc_handle* h, void* ev);
+int  a1mpc_event_record(a1mpc_handle* h, void* ev);                  /* on the handle's stream */
+int  a1mpc_event_elapsed_ms(a1mpc_handle* h, void* start, void* stop, float* ms); /* syncs on stop */
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+int64_t a1mpc_launch_count(const a1mpc_handle* h);
+/* measured peak of the fp64 FMA pipe on this device, TFLOP/s (dependent-free DFMA stream) */
+int  a1mpc_measure_fp64_peak(a1mpc_handle* h, double* tflops);
+/* writes one buffer larger than L2 (flushes L2 between timed iterations when asked to) */
+int  a1mpc_flush_l2(a1mpc_handle* h);
+
+/* ---- optional final collect across GPUs: all-gather of f_body over NCCL ------- */
+/* NCCL is dlopen'ed at first use; without it these return A1MPC_ENCCL and nothing else in the
+ * library depends on it.  unique_id is a 128-byte ncclUniqueId produced on rank 0. */
+int  a1mpc_nccl_unique_id(void* unique_id128);
+int  a1mpc_nccl_init(a1mpc_handle* h, int nranks, int rank, const void* unique_id128);
+/* gathers f_local [12][B_local] (device) from every rank into f_all [nranks][12][B_local] */
+int  a1mpc_allgather_forces(a1mpc_handle* h, const double* f_local, double* f_all, int B_local);
+
+/* ---- synthetic workload generator, host-side, deterministic ------------------- */
+/* Fills host SoA arrays (ld = B) with the trot-gait state distribution of the benchmark.
+ * config_id: 2 = trot narrow noise (configs 2,3,5), 4 = wide noise (config 4's state noise).
+ * seed = 0xA1C0FFEE + config_id + `stream` (use the rank / batch index as stream). */
+int  a1mpc_gen_states(int config_id, uint64_t stream, int B, double* x0, double* rot, double* foot,
+                      double* ref, uint32_t* contact);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* A1MPC_H_ */

@@ -1,0 +1,1151 @@
+// oracle/a1mpc_oracle.cpp -- TEST INFRASTRUCTURE, not product code.
+//
+// CPU restatement of the reference hot path (ShuoYangRobotics/A1-QP-MPC-Controller), used only
+// as the checker by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs.  Nothing under a1-qp-mpc-controller_b200/ may include, link or call this file.
+//
+// PARITY UNPINNED: the reference holds no golden vector, known-answer test or fixture for this
+// path (test/test_mpc.cpp:157-161 prints and returns 0) and its arithmetic lives in third-party
+// OSQP (github.com/oxfordcontrol/osqp, unpinned master ~v0.6.2, docker/Dockerfile:77-83) behind
+// osqp-eigen (unpinned, build log 0.6.3, docker/Dockerfile:91-98); neither Eigen, OSQP nor ROS is
+// installable offline, so the reference itself cannot be compiled here (oracle/_ref is absent).
+// What pins this file instead: (1) two independent solvers below agree (OSQP-algorithm restatement
+// run to eps 1e-11 vs. long-double exact solver) and (2) every exact solution carries a KKT
+// certificate evaluated on the LITERAL 12N-variable problem, which is a proof of optimality that
+// does not depend on how the point was found (H is positive definite: 2r > 0).
+//
+// Dependency-free C++17.  Literal where the reference is literal: dense rollout, dense
+// B_qp^T Q B_qp, dense constraint matrix, OSQP-style ADMM.  No closed forms, no swing elimination
+// in the reference-faithful path.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../include/a1mpc.h"
+
+namespace {
+
+typedef long double ld;
+const double OSQP_INFTY = 1e30;  // OsqpEigen::INFTY (osqp's OSQP_INFTY), used by ConvexMpc.cpp:230-237
+
+// ------------------------------------------------------------------------------------------
+// tiny dense helpers (row-major)
+// ------------------------------------------------------------------------------------------
+struct Mat {
+  int r = 0, c = 0;
+  std::vector<double> a;
+  Mat() {}
+  Mat(int r_, int c_) : r(r_), c(c_), a((size_t)r_ * c_, 0.0) {}
+  double& operator()(int i, int j) { return a[(size_t)i * c + j]; }
+  double operator()(int i, int j) const { return a[(size_t)i * c + j]; }
+};
+
+static void mat3_mul(const double* A, const double* B, double* C) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += A[3 * i + k] * B[3 * k + j];
+      C[3 * i + j] = s;
+    }
+}
+static void mat3_T(const double* A, double* B) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) B[3 * j + i] = A[3 * i + j];
+}
+static void mat3_inv(const double* m, double* o) {
+  double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
+               m[2] * (m[3] * m[7] - m[4] * m[6]);
+  double id = 1.0 / det;
+  o[0] = (m[4] * m[8] - m[5] * m[7]) * id;
+  o[1] = (m[2] * m[7] - m[1] * m[8]) * id;
+  o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+  o[3] = (m[5] * m[6] - m[3] * m[8]) * id;
+  o[4] = (m[0] * m[8] - m[2] * m[6]) * id;
+  o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+  o[6] = (m[3] * m[7] - m[4] * m[6]) * id;
+  o[7] = (m[1] * m[6] - m[0] * m[7]) * id;
+  o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+}
+// Utils::skew, utils/Utils.cpp:35-41
+static void skew(const double* v, double* S) {
+  S[0] = 0;     S[1] = -v[2]; S[2] = v[1];
+  S[3] = v[2];  S[4] = 0;     S[5] = -v[0];
+  S[6] = -v[1]; S[7] = v[0];  S[8] = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// ConvexMpc restated (ConvexMpc.cpp:7-260), horizon N at run time
+// ------------------------------------------------------------------------------------------
+struct ConvexMpcRestated {
+  int N;
+  double mu, fz_min, fz_max;
+  std::vector<double> q_weights_mpc, r_weights_mpc;  // tiled, un-doubled (ConvexMpc.cpp:16-19, 37-40)
+  Mat linear_constraints;                            // 20N x 12N (ConvexMpc.cpp:46-58)
+  Mat A_mat_c, B_mat_c, A_mat_d, B_mat_d, B_mat_d_list, A_qp, B_qp, hessian;
+  std::vector<double> gradient, lb, ub;
+
+  ConvexMpcRestated(int N_, const double* q, const double* r, double mu_, double fzmin, double fzmax)
+      : N(N_), mu(mu_), fz_min(fzmin), fz_max(fzmax) {
+    q_weights_mpc.resize(13 * N);
+    r_weights_mpc.resize(12 * N);
+    for (int i = 0; i < N; ++i) {
+      for (int k = 0; k < 13; ++k) q_weights_mpc[13 * i + k] = q[k];
+      for (int k = 0; k < 12; ++k) r_weights_mpc[12 * i + k] = r[k];
+    }
+    linear_constraints = Mat(20 * N, 12 * N);
+    for (int i = 0; i < 4 * N; ++i) {
+      linear_constraints(0 + 5 * i, 0 + 3 * i) = 1;
+      linear_constraints(1 + 5 * i, 0 + 3 * i) = 1;
+      linear_constraints(2 + 5 * i, 1 + 3 * i) = 1;
+      linear_constraints(3 + 5 * i, 1 + 3 * i) = 1;
+      linear_constraints(4 + 5 * i, 2 + 3 * i) = 1;
+      linear_constraints(0 + 5 * i, 2 + 3 * i) = mu;
+      linear_constraints(1 + 5 * i, 2 + 3 * i) = -mu;
+      linear_constraints(2 + 5 * i, 2 + 3 * i) = mu;
+      linear_constraints(3 + 5 * i, 2 + 3 * i) = -mu;
+    }
+    reset();
+  }
+  void reset() {  // ConvexMpc.cpp:70-108
+    A_mat_c = Mat(13, 13); B_mat_c = Mat(13, 12); A_mat_d = Mat(13, 13); B_mat_d = Mat(13, 12);
+    B_mat_d_list = Mat(13 * N, 12); A_qp = Mat(13 * N, 13); B_qp = Mat(13 * N, 12 * N);
+    hessian = Mat(12 * N, 12 * N);
+    gradient.assign(12 * N, 0.0); lb.assign(20 * N, 0.0); ub.assign(20 * N, 0.0);
+  }
+  void calculate_A_mat_c(const double* root_euler) {  // ConvexMpc.cpp:110-130
+    double cy = std::cos(root_euler[2]), sy = std::sin(root_euler[2]);
+    A_mat_c(0, 6) = cy;  A_mat_c(0, 7) = sy; A_mat_c(0, 8) = 0;
+    A_mat_c(1, 6) = -sy; A_mat_c(1, 7) = cy; A_mat_c(1, 8) = 0;
+    A_mat_c(2, 6) = 0;   A_mat_c(2, 7) = 0;  A_mat_c(2, 8) = 1;
+    for (int k = 0; k < 3; ++k) A_mat_c(3 + k, 9 + k) = 1;
+    A_mat_c(11, 12) = 1;
+  }
+  void calculate_B_mat_c(double mass, const double* inertia, const double* R, const double* foot /*3x4 row-major*/) {
+    // ConvexMpc.cpp:132-143
+    double RT[9], t[9], Iw[9], Iwinv[9];
+    mat3_T(R, RT);
+    mat3_mul(R, inertia, t);
+    mat3_mul(t, RT, Iw);
+    for (int i = 0; i < 4; ++i) {
+      mat3_inv(Iw, Iwinv);  // the reference inverts once per leg
+      double v[3] = {foot[0 * 4 + i], foot[1 * 4 + i], foot[2 * 4 + i]}, S[9], M[9];
+      skew(v, S);
+      mat3_mul(Iwinv, S, M);
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+          B_mat_c(6 + a, 3 * i + b) = M[3 * a + b];
+          B_mat_c(9 + a, 3 * i + b) = (a == b) ? (1 / mass) : 0.0;
+        }
+    }
+  }
+  void state_space_discretization(double dt) {  // ConvexMpc.cpp:145-156 (forward Euler)
+    for (int i = 0; i < 13; ++i)
+      for (int j = 0; j < 13; ++j) A_mat_d(i, j) = (i == j ? 1.0 : 0.0) + A_mat_c(i, j) * dt;
+    for (int i = 0; i < 13; ++i)
+      for (int j = 0; j < 12; ++j) B_mat_d(i, j) = B_mat_c(i, j) * dt;
+  }
+  void store_B(int i) {  // A1RobotControl.cpp:513
+    for (int a = 0; a < 13; ++a)
+      for (int b = 0; b < 12; ++b) B_mat_d_list(13 * i + a, b) = B_mat_d(a, b);
+  }
+  // ConvexMpc.cpp:158-245
+  void calculate_qp_mats(const double* mpc_states, const double* mpc_states_d, const bool* contacts) {
+    const int nx = 13, nu = 12;
+    // rollout :184-202
+    for (int i = 0; i < N; ++i) {
+      if (i == 0) {
+        for (int a = 0; a < nx; ++a)
+          for (int b = 0; b < nx; ++b) A_qp(a, b) = A_mat_d(a, b);
+      } else {
+        for (int a = 0; a < nx; ++a)
+          for (int b = 0; b < nx; ++b) {
+            double s = 0;
+            for (int k = 0; k < nx; ++k) s += A_qp(nx * (i - 1) + a, k) * A_mat_d(k, b);
+            A_qp(nx * i + a, b) = s;
+          }
+      }
+      for (int j = 0; j < i + 1; ++j) {
+        if (i - j == 0) {
+          for (int a = 0; a < nx; ++a)
+            for (int b = 0; b < nu; ++b) B_qp(nx * i + a, nu * j + b) = B_mat_d_list(nx * j + a, b);
+        } else {
+          for (int a = 0; a < nx; ++a)
+            for (int b = 0; b < nu; ++b) {
+              double s = 0;
+              for (int k = 0; k < nx; ++k) s += A_qp(nx * (i - j - 1) + a, k) * B_mat_d_list(nx * j + k, b);
+              B_qp(nx * i + a, nu * j + b) = s;
+            }
+        }
+      }
+    }
+    // hessian :207-211   dense_hessian = B_qp^T * Q * B_qp ; += R   with Q = 2 q, R = 2 r
+    const int n = nu * N, ns = nx * N;
+    Mat QB(ns, n);
+    for (int i = 0; i < ns; ++i) {
+      double w = 2 * q_weights_mpc[i];
+      for (int j = 0; j < n; ++j) QB(i, j) = w * B_qp(i, j);
+    }
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) hessian(i, j) = 0;
+    for (int k = 0; k < ns; ++k) {
+      const double* bk = &B_qp.a[(size_t)k * n];
+      const double* qk = &QB.a[(size_t)k * n];
+      for (int i = 0; i < n; ++i) {
+        double bi = bk[i];
+        if (bi == 0.0) continue;
+        double* hi = &hessian.a[(size_t)i * n];
+        for (int j = 0; j < n; ++j) hi[j] += bi * qk[j];
+      }
+    }
+    for (int i = 0; i < n; ++i) hessian(i, i) += 2 * r_weights_mpc[i];
+    // gradient :215-217
+    std::vector<double> tmp(ns);
+    for (int i = 0; i < ns; ++i) {
+      double s = 0;
+      for (int k = 0; k < nx; ++k) s += A_qp(i, k) * mpc_states[k];
+      tmp[i] = (s - mpc_states_d[i]) * 2 * q_weights_mpc[i];
+    }
+    for (int j = 0; j < n; ++j) {
+      double s = 0;
+      for (int i = 0; i < ns; ++i) s += B_qp(i, j) * tmp[i];
+      gradient[j] = s;
+    }
+    // bounds :223-245
+    double lb1[20], ub1[20];
+    for (int i = 0; i < 4; ++i) {
+      double c = contacts[i] ? 1.0 : 0.0;
+      lb1[5 * i + 0] = 0;           ub1[5 * i + 0] = OSQP_INFTY;
+      lb1[5 * i + 1] = -OSQP_INFTY; ub1[5 * i + 1] = 0;
+      lb1[5 * i + 2] = 0;           ub1[5 * i + 2] = OSQP_INFTY;
+      lb1[5 * i + 3] = -OSQP_INFTY; ub1[5 * i + 3] = 0;
+      lb1[5 * i + 4] = fz_min * c;  ub1[5 * i + 4] = fz_max * c;
+    }
+    for (int i = 0; i < N; ++i)
+      for (int k = 0; k < 20; ++k) { lb[20 * i + k] = lb1[k]; ub[20 * i + k] = ub1[k]; }
+  }
+};
+
+// one robot's record, unpacked from the SoA batch
+struct RobotState {
+  double euler[3], pos[3], ang_vel[3], lin_vel[3];
+  double R[9];
+  double foot[12];  // 3x4 row-major like Eigen's operator<< listing: foot[a*4 + leg]
+  double euler_d01[2], ang_vel_d[3], lin_vel_d[3], pos_d_z;
+  bool contacts[4];
+};
+static void unpack(const a1mpc_inputs* in, int b, RobotState* s) {
+  size_t ld_ = in->ld;
+  for (int k = 0; k < 3; ++k) {
+    s->euler[k] = in->x0[(0 + k) * ld_ + b];
+    s->pos[k] = in->x0[(3 + k) * ld_ + b];
+    s->ang_vel[k] = in->x0[(6 + k) * ld_ + b];
+    s->lin_vel[k] = in->x0[(9 + k) * ld_ + b];
+  }
+  for (int k = 0; k < 9; ++k) s->R[k] = in->rot[k * ld_ + b];
+  for (int leg = 0; leg < 4; ++leg)
+    for (int a = 0; a < 3; ++a) s->foot[a * 4 + leg] = in->foot[(3 * leg + a) * ld_ + b];
+  s->euler_d01[0] = in->ref[0 * ld_ + b];
+  s->euler_d01[1] = in->ref[1 * ld_ + b];
+  for (int k = 0; k < 3; ++k) {
+    s->ang_vel_d[k] = in->ref[(2 + k) * ld_ + b];
+    s->lin_vel_d[k] = in->ref[(5 + k) * ld_ + b];
+  }
+  s->pos_d_z = in->ref[8 * ld_ + b];
+  for (int i = 0; i < 4; ++i) s->contacts[i] = (in->contact[b] >> i) & 1u;
+}
+
+// A1RobotControl::compute_grf, MPC branch up to calculate_qp_mats (A1RobotControl.cpp:447-518)
+static void drive_convex_mpc(ConvexMpcRestated& mpc, const a1mpc_config& cfg, const RobotState& st,
+                             std::vector<double>& mpc_states, std::vector<double>& mpc_states_d) {
+  const int N = cfg.horizon;
+  mpc.reset();
+  mpc_states.assign(13, 0.0);
+  for (int k = 0; k < 3; ++k) {
+    mpc_states[k] = st.euler[k];
+    mpc_states[3 + k] = st.pos[k];
+    mpc_states[6 + k] = st.ang_vel[k];
+    mpc_states[9 + k] = st.lin_vel[k];
+  }
+  mpc_states[12] = -9.8;
+  double mpc_dt = cfg.dt;
+  double vdw[3];
+  for (int a = 0; a < 3; ++a)
+    vdw[a] = st.R[3 * a + 0] * st.lin_vel_d[0] + st.R[3 * a + 1] * st.lin_vel_d[1] + st.R[3 * a + 2] * st.lin_vel_d[2];
+  mpc_states_d.assign(13 * N, 0.0);
+  for (int i = 0; i < N; ++i) {  // :472-488
+    double* d = &mpc_states_d[13 * i];
+    d[0] = st.euler_d01[0];
+    d[1] = st.euler_d01[1];
+    d[2] = st.euler[2] + st.ang_vel_d[2] * mpc_dt * (i + 1);
+    d[3] = st.pos[0] + vdw[0] * mpc_dt * (i + 1);
+    d[4] = st.pos[1] + vdw[1] * mpc_dt * (i + 1);
+    d[5] = st.pos_d_z;
+    d[6] = st.ang_vel_d[0];
+    d[7] = st.ang_vel_d[1];
+    d[8] = st.ang_vel_d[2];
+    d[9] = vdw[0];
+    d[10] = vdw[1];
+    d[11] = 0;
+    d[12] = -9.8;
+  }
+  mpc.calculate_A_mat_c(st.euler);
+  for (int i = 0; i < N; ++i) {  // :498-514, same inputs every i
+    mpc.calculate_B_mat_c(cfg.mass, cfg.inertia, st.R, st.foot);
+    mpc.state_space_discretization(mpc_dt);
+    mpc.store_B(i);
+  }
+  mpc.calculate_qp_mats(mpc_states.data(), mpc_states_d.data(), st.contacts);
+}
+
+// ------------------------------------------------------------------------------------------
+// OSQP algorithm restated (osqp 0.6.x defaults).  Dense P, row-sparse A.
+// The KKT system [P+sigma I, A'; A, -1/rho] is solved in its reduced form
+// (P + sigma I + A' diag(rho) A) x = rhs_x + A' diag(rho) rhs_z, which is the same linear map.
+// ------------------------------------------------------------------------------------------
+struct OsqpSettings {
+  double rho = 0.1, sigma = 1e-6, alpha = 1.6, eps_abs = 1e-3, eps_rel = 1e-3;
+  int max_iter = 4000, scaling = 10, check_termination = 25, adaptive_rho = 1, adaptive_rho_interval = 25;
+  double adaptive_rho_tolerance = 5.0;
+};
+struct OsqpInfo { int iter = 0; int status = 0; /*1 solved, 2 max_iter*/ double pri_res = 0, dua_res = 0; int rho_updates = 0; };
+
+struct SparseRows {  // A in row lists
+  int m = 0, n = 0;
+  std::vector<int> ptr, idx;
+  std::vector<double> val;
+  void from_dense(const Mat& A) {
+    m = A.r; n = A.c; ptr.assign(1, 0); idx.clear(); val.clear();
+    for (int i = 0; i < m; ++i) {
+      for (int j = 0; j < n; ++j)
+        if (A(i, j) != 0.0) { idx.push_back(j); val.push_back(A(i, j)); }
+      ptr.push_back((int)idx.size());
+    }
+  }
+};
+
+static bool chol_factor(std::vector<double>& K, int n) {  // in place lower, row-major
+  for (int j = 0; j < n; ++j) {
+    double d = K[(size_t)j * n + j];
+    for (int k = 0; k < j; ++k) d -= K[(size_t)j * n + k] * K[(size_t)j * n + k];
+    if (!(d > 0)) return false;
+    d = std::sqrt(d);
+    K[(size_t)j * n + j] = d;
+    for (int i = j + 1; i < n; ++i) {
+      double s = K[(size_t)i * n + j];
+      const double* ri = &K[(size_t)i * n];
+      const double* rj = &K[(size_t)j * n];
+      for (int k = 0; k < j; ++k) s -= ri[k] * rj[k];
+      K[(size_t)i * n + j] = s / d;
+    }
+  }
+  return true;
+}
+static void chol_solve(const std::vector<double>& L, int n, double* b) {
+  for (int i = 0; i < n; ++i) {
+    double s = b[i];
+    const double* ri = &L[(size_t)i * n];
+    for (int k = 0; k < i; ++k) s -= ri[k] * b[k];
+    b[i] = s / ri[i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = b[i];
+    for (int k = i + 1; k < n; ++k) s -= L[(size_t)k * n + i] * b[k];
+    b[i] = s / L[(size_t)i * n + i];
+  }
+}
+static double norm_inf(const double* v, int n) {
+  double m = 0;
+  for (int i = 0; i < n; ++i) m = std::max(m, std::fabs(v[i]));
+  return m;
+}
+static void limit_scaling(double* v, int n) {
+  for (int i = 0; i < n; ++i) {
+    v[i] = v[i] < 1e-4 ? 1.0 : v[i];
+    v[i] = v[i] > 1e4 ? 1e4 : v[i];
+  }
+}
+
+static void osqp_restated_solve(int n, int m, const Mat& P_in, const double* q_in, const SparseRows& A_in,
+                                const double* l_in, const double* u_in, const OsqpSettings& st,
+                                double* x_out, OsqpInfo* info) {
+  // ---- scale_data (osqp/src/scaling.c) ----
+  Mat P = P_in;
+  SparseRows A = A_in;
+  std::vector<double> q(q_in, q_in + n), l(l_in, l_in + m), u(u_in, u_in + m);
+  std::vector<double> D(n, 1.0), E(m, 1.0), Dt(n), Et(m);
+  double c = 1.0;
+  for (int it = 0; it < st.scaling; ++it) {
+    for (int j = 0; j < n; ++j) Dt[j] = 0;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) Dt[j] = std::max(Dt[j], std::fabs(P(i, j)));
+    for (int i = 0; i < m; ++i) {
+      double rn = 0;
+      for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) {
+        rn = std::max(rn, std::fabs(A.val[k]));
+        Dt[A.idx[k]] = std::max(Dt[A.idx[k]], std::fabs(A.val[k]));
+      }
+      Et[i] = rn;
+    }
+    limit_scaling(Dt.data(), n);
+    limit_scaling(Et.data(), m);
+    for (int j = 0; j < n; ++j) Dt[j] = 1.0 / std::sqrt(Dt[j]);
+    for (int i = 0; i < m; ++i) Et[i] = 1.0 / std::sqrt(Et[i]);
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) P(i, j) *= Dt[i] * Dt[j];
+    for (int i = 0; i < m; ++i)
+      for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) A.val[k] *= Et[i] * Dt[A.idx[k]];
+    for (int j = 0; j < n; ++j) { q[j] *= Dt[j]; D[j] *= Dt[j]; }
+    for (int i = 0; i < m; ++i) E[i] *= Et[i];
+    // cost scaling
+    double mean = 0;
+    for (int j = 0; j < n; ++j) {
+      double cn = 0;
+      for (int i = 0; i < n; ++i) cn = std::max(cn, std::fabs(P(i, j)));
+      mean += cn;
+    }
+    mean /= n;
+    double nq = norm_inf(q.data(), n);
+    limit_scaling(&nq, 1);
+    double ct = std::max(mean, nq);
+    limit_scaling(&ct, 1);
+    ct = 1.0 / ct;
+    for (auto& v : P.a) v *= ct;
+    for (auto& v : q) v *= ct;
+    c *= ct;
+  }
+  for (int i = 0; i < m; ++i) { l[i] *= E[i]; u[i] *= E[i]; }
+  const double cinv = 1.0 / c;
+
+  // ---- rho vector (osqp/src/auxil.c set_rho_vec) ----
+  std::vector<int> ctype(m);
+  std::vector<double> rho_vec(m);
+  double rho = st.rho;
+  auto set_rho_vec = [&]() {
+    for (int i = 0; i < m; ++i) {
+      if (l[i] < -OSQP_INFTY * 1e-4 && u[i] > OSQP_INFTY * 1e-4) { ctype[i] = -1; rho_vec[i] = 1e-6; }
+      else if (u[i] - l[i] < 1e-4) { ctype[i] = 1; rho_vec[i] = 1e3 * rho; }
+      else { ctype[i] = 0; rho_vec[i] = rho; }
+    }
+  };
+  set_rho_vec();
+  std::vector<double> K((size_t)n * n);
+  auto factor = [&]() {
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) K[(size_t)i * n + j] = P(i, j) + (i == j ? st.sigma : 0.0);
+    for (int i = 0; i < m; ++i)
+      for (int k1 = A.ptr[i]; k1 < A.ptr[i + 1]; ++k1)
+        for (int k2 = A.ptr[i]; k2 < A.ptr[i + 1]; ++k2)
+          K[(size_t)A.idx[k1] * n + A.idx[k2]] += rho_vec[i] * A.val[k1] * A.val[k2];
+    chol_factor(K, n);
+  };
+  factor();
+
+  std::vector<double> x(n, 0.0), z(m, 0.0), y(m, 0.0), xp(n), zp(m), xt(n), zt(m), Ax(m), Px(n), Aty(n), rhs(n);
+  auto mulA = [&](const double* v, double* out) {
+    for (int i = 0; i < m; ++i) {
+      double s = 0;
+      for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) s += A.val[k] * v[A.idx[k]];
+      out[i] = s;
+    }
+  };
+  auto mulAt = [&](const double* v, double* out) {
+    for (int j = 0; j < n; ++j) out[j] = 0;
+    for (int i = 0; i < m; ++i)
+      for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) out[A.idx[k]] += A.val[k] * v[i];
+  };
+  auto mulP = [&](const double* v, double* out) {
+    for (int i = 0; i < n; ++i) {
+      double s = 0;
+      const double* pi = &P.a[(size_t)i * n];
+      for (int j = 0; j < n; ++j) s += pi[j] * v[j];
+      out[i] = s;
+    }
+  };
+  double pri_res = 0, dua_res = 0;
+  auto residuals = [&](bool scaled, double* eps_pri, double* eps_dua) {
+    // update_info + check_termination thresholds (osqp/src/auxil.c compute_pri_res/compute_dua_res/...)
+    mulA(x.data(), Ax.data());
+    mulP(x.data(), Px.data());
+    mulAt(y.data(), Aty.data());
+    double pr = 0, nAx = 0, nz = 0;
+    for (int i = 0; i < m; ++i) {
+      double s = scaled ? 1.0 : 1.0 / E[i];
+      pr = std::max(pr, std::fabs(s * (Ax[i] - z[i])));
+      nAx = std::max(nAx, std::fabs(s * Ax[i]));
+      nz = std::max(nz, std::fabs(s * z[i]));
+    }
+    double dr = 0, nPx = 0, nAty = 0, nq = 0;
+    for (int j = 0; j < n; ++j) {
+      double s = scaled ? 1.0 : 1.0 / D[j];
+      dr = std::max(dr, std::fabs(s * (Px[j] + q[j] + Aty[j])));
+      nPx = std::max(nPx, std::fabs(s * Px[j]));
+      nAty = std::max(nAty, std::fabs(s * Aty[j]));
+      nq = std::max(nq, std::fabs(s * q[j]));
+    }
+    if (!scaled) { dr *= cinv; nPx *= cinv; nAty *= cinv; nq *= cinv; }
+    pri_res = pr; dua_res = dr;
+    if (eps_pri) *eps_pri = st.eps_abs + st.eps_rel * std::max(nAx, nz);
+    if (eps_dua) *eps_dua = st.eps_abs + st.eps_rel * std::max(std::max(nPx, nAty), nq);
+    return std::make_pair(std::max(nAx, nz), std::max(std::max(nPx, nAty), nq));
+  };
+  int iter;
+  bool solved = false;
+  for (iter = 1; iter <= st.max_iter; ++iter) {
+    xp = x; zp = z;
+    // update_xz_tilde
+    for (int j = 0; j < n; ++j) rhs[j] = st.sigma * xp[j] - q[j];
+    for (int i = 0; i < m; ++i) {
+      double rz = zp[i] - y[i] / rho_vec[i];
+      double w = rho_vec[i] * rz;
+      for (int k = A.ptr[i]; k < A.ptr[i + 1]; ++k) rhs[A.idx[k]] += A.val[k] * w;
+    }
+    chol_solve(K, n, rhs.data());
+    xt = rhs;
+    mulA(xt.data(), zt.data());  // reduced form: z_tilde = A x_tilde
+    // update_x, update_z, update_y
+    for (int j = 0; j < n; ++j) x[j] = st.alpha * xt[j] + (1 - st.alpha) * xp[j];
+    for (int i = 0; i < m; ++i) {
+      double v = st.alpha * zt[i] + (1 - st.alpha) * zp[i];
+      double zz = v + y[i] / rho_vec[i];
+      zz = std::min(std::max(zz, l[i]), u[i]);
+      z[i] = zz;
+      y[i] += rho_vec[i] * (v - zz);
+    }
+    bool can_check = st.check_termination && (iter % st.check_termination == 0);
+    if (can_check) {
+      double ep, ed;
+      residuals(false, &ep, &ed);
+      if (pri_res <= ep && dua_res <= ed) { solved = true; break; }
+    }
+    if (st.adaptive_rho && st.adaptive_rho_interval && (iter % st.adaptive_rho_interval == 0)) {
+      auto nn = residuals(true, nullptr, nullptr);  // compute_rho_estimate works on scaled quantities
+      double pr = pri_res / (nn.first + 1e-10), dr = dua_res / (nn.second + 1e-10);
+      double rho_new = rho * std::sqrt(pr / (dr + 1e-10));
+      rho_new = std::min(std::max(rho_new, 1e-6), 1e6);
+      if (rho_new > rho * st.adaptive_rho_tolerance || rho_new < rho / st.adaptive_rho_tolerance) {
+        rho = rho_new;
+        set_rho_vec();
+        factor();
+        info->rho_updates++;
+      }
+    }
+  }
+  if (!solved) {
+    if (iter > st.max_iter) iter = st.max_iter;
+    double ep, ed;
+    residuals(false, &ep, &ed);
+    solved = pri_res <= ep && dua_res <= ed;
+  }
+  for (int j = 0; j < n; ++j) x_out[j] = D[j] * x[j];  // unscale_solution
+  info->iter = iter;
+  info->status = solved ? 1 : 2;
+  info->pri_res = pri_res;
+  info->dua_res = dua_res;
+}
+
+// ------------------------------------------------------------------------------------------
+// Exact solver (long double): Mehrotra IPM on the swing-eliminated QP followed by an active-set
+// finish, then a KKT certificate on the LITERAL problem (P, q, A, l, u).
+// ------------------------------------------------------------------------------------------
+static bool ld_chol(std::vector<ld>& K, int n) {
+  for (int j = 0; j < n; ++j) {
+    ld d = K[(size_t)j * n + j];
+    for (int k = 0; k < j; ++k) d -= K[(size_t)j * n + k] * K[(size_t)j * n + k];
+    if (!(d > 0)) return false;
+    d = sqrtl(d);
+    K[(size_t)j * n + j] = d;
+    for (int i = j + 1; i < n; ++i) {
+      ld s = K[(size_t)i * n + j];
+      for (int k = 0; k < j; ++k) s -= K[(size_t)i * n + k] * K[(size_t)j * n + k];
+      K[(size_t)i * n + j] = s / d;
+    }
+  }
+  return true;
+}
+static void ld_chol_solve(const std::vector<ld>& L, int n, ld* b) {
+  for (int i = 0; i < n; ++i) {
+    ld s = b[i];
+    for (int k = 0; k < i; ++k) s -= L[(size_t)i * n + k] * b[k];
+    b[i] = s / L[(size_t)i * n + i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    ld s = b[i];
+    for (int k = i + 1; k < n; ++k) s -= L[(size_t)k * n + i] * b[k];
+    b[i] = s / L[(size_t)i * n + i];
+  }
+}
+
+struct ExactInfo { int ipm_iters = 0, rounds = 0, verified = 0; double kkt_stat = 0, kkt_prim = 0, kkt_dual = 0; };
+
+// reduced problem: n = 3K variables, K foot-steps; constraints per foot-step, C u <= d:
+//   -fx - mu fz <= 0, fx - mu fz <= 0, -fy - mu fz <= 0, fy - mu fz <= 0, fz <= fzmax, -fz <= -fzmin
+static bool exact_reduced(int n, const std::vector<ld>& H, const std::vector<ld>& g, ld mu_f, ld fzmin, ld fzmax,
+                          std::vector<ld>& u_out, ExactInfo* info) {
+  const int K = n / 3, m = 6 * K;
+  // scaling as in any sane IPM: forces in units of fs, cost by max|H|
+  const ld fs = 100.0L;
+  ld cs = 0;
+  for (auto v : H) cs = std::max(cs, fabsl(v));
+  cs *= fs * fs;
+  std::vector<ld> Hs((size_t)n * n), gs(n);
+  for (size_t i = 0; i < Hs.size(); ++i) Hs[i] = H[i] * fs * fs / cs;
+  for (int i = 0; i < n; ++i) gs[i] = g[i] * fs / cs;
+  const ld dmax = fzmax / fs, dmin = fzmin / fs;
+  auto Crow = [&](int r, ld* c3) {  // row r%6 of a foot-step block
+    switch (r) {
+      case 0: c3[0] = -1; c3[1] = 0; c3[2] = -mu_f; break;
+      case 1: c3[0] = 1; c3[1] = 0; c3[2] = -mu_f; break;
+      case 2: c3[0] = 0; c3[1] = -1; c3[2] = -mu_f; break;
+      case 3: c3[0] = 0; c3[1] = 1; c3[2] = -mu_f; break;
+      case 4: c3[0] = 0; c3[1] = 0; c3[2] = 1; break;
+      default: c3[0] = 0; c3[1] = 0; c3[2] = -1; break;
+    }
+  };
+  auto dval = [&](int r) -> ld { return r == 4 ? dmax : (r == 5 ? -dmin : 0.0L); };
+  std::vector<ld> x(n, 0.0L), s(m), lam(m), rd(n), rp(m), w(m), Kmat((size_t)n * n), rhs(n), dxa(n), dsa(m), dla(m),
+      dx(n), ds(m), dl(m), rc(m);
+  for (int k = 0; k < K; ++k) x[3 * k + 2] = 0.5L * (dmin + dmax) * 0.5L + 0.5L * dmin;
+  ld gmax = 0;
+  for (auto v : gs) gmax = std::max(gmax, fabsl(v));
+  for (int k = 0; k < K; ++k)
+    for (int r = 0; r < 6; ++r) {
+      ld c3[3];
+      Crow(r, c3);
+      ld cu = c3[0] * x[3 * k] + c3[1] * x[3 * k + 1] + c3[2] * x[3 * k + 2];
+      s[6 * k + r] = std::max(dval(r) - cu, (ld)1e-2L);
+      lam[6 * k + r] = gmax + 1e-3L;
+    }
+  auto amax = [&](const std::vector<ld>& v, const std::vector<ld>& dv) {
+    ld a = 1;
+    for (int i = 0; i < m; ++i)
+      if (dv[i] < 0) a = std::min(a, -v[i] / dv[i]);
+    return a;
+  };
+  // face states for the finisher
+  std::vector<int> zx(K), zy(K), zz(K);
+  auto finisher = [&](int maxround) -> bool {
+    const ld tol = 1e-15L;
+    std::vector<ld> Z((size_t)n * n), c(n), M((size_t)n * n), y(n), u(n), r(n), t1(n);
+    std::vector<char> fixed(n);
+    for (int rnd = 0; rnd < maxround; ++rnd) {
+      info->rounds++;
+      std::fill(Z.begin(), Z.end(), 0.0L);
+      std::fill(c.begin(), c.end(), 0.0L);
+      std::fill(fixed.begin(), fixed.end(), 0);
+      for (int k = 0; k < K; ++k) {
+        int ix = 3 * k, iy = ix + 1, iz = ix + 2;
+        if (zz[k] == -1) {  // pinned at fz = fzmin ... only a vertex when fzmin == 0
+          fixed[iz] = 1; c[iz] = dmin;
+          if (dmin == 0) { fixed[ix] = fixed[iy] = 1; continue; }
+          if (zx[k]) { fixed[ix] = 1; c[ix] = zx[k] * mu_f * dmin; } else Z[(size_t)ix * n + ix] = 1;
+          if (zy[k]) { fixed[iy] = 1; c[iy] = zy[k] * mu_f * dmin; } else Z[(size_t)iy * n + iy] = 1;
+          continue;
+        }
+        if (zz[k] == 0) {
+          Z[(size_t)iz * n + iz] = 1;
+          if (zx[k]) { Z[(size_t)ix * n + iz] = zx[k] * mu_f; fixed[ix] = 1; } else Z[(size_t)ix * n + ix] = 1;
+          if (zy[k]) { Z[(size_t)iy * n + iz] = zy[k] * mu_f; fixed[iy] = 1; } else Z[(size_t)iy * n + iy] = 1;
+        } else {
+          fixed[iz] = 1; c[iz] = dmax;
+          if (zx[k]) { c[ix] = zx[k] * mu_f * dmax; fixed[ix] = 1; } else Z[(size_t)ix * n + ix] = 1;
+          if (zy[k]) { c[iy] = zy[k] * mu_f * dmax; fixed[iy] = 1; } else Z[(size_t)iy * n + iy] = 1;
+        }
+      }
+      // M = Z' Hs Z + diag(fixed), rhs = -Z'(gs + Hs c)
+      std::vector<ld> HZ((size_t)n * n, 0.0L);
+      for (int i = 0; i < n; ++i)
+        for (int kk = 0; kk < n; ++kk) {
+          ld h = Hs[(size_t)i * n + kk];
+          if (h == 0) continue;
+          int k0 = 3 * (kk / 3);
+          for (int j = k0; j < k0 + 3; ++j)
+            if (Z[(size_t)kk * n + j] != 0) HZ[(size_t)i * n + j] += h * Z[(size_t)kk * n + j];
+        }
+      std::fill(M.begin(), M.end(), 0.0L);
+      for (int kk = 0; kk < n; ++kk) {
+        int k0 = 3 * (kk / 3);
+        for (int i = k0; i < k0 + 3; ++i) {
+          ld zki = Z[(size_t)kk * n + i];
+          if (zki == 0) continue;
+          for (int j = 0; j < n; ++j) M[(size_t)i * n + j] += zki * HZ[(size_t)kk * n + j];
+        }
+      }
+      for (int i = 0; i < n; ++i)
+        if (fixed[i]) M[(size_t)i * n + i] += 1;
+      for (int i = 0; i < n; ++i) {
+        ld sacc = gs[i];
+        for (int j = 0; j < n; ++j) sacc += Hs[(size_t)i * n + j] * c[j];
+        t1[i] = sacc;
+      }
+      for (int j = 0; j < n; ++j) {
+        ld sacc = 0;
+        int k0 = 3 * (j / 3);
+        for (int i = k0; i < k0 + 3; ++i) sacc += Z[(size_t)i * n + j] * t1[i];
+        y[j] = -sacc;
+      }
+      if (!ld_chol(M, n)) return false;
+      ld_chol_solve(M, n, y.data());
+      for (int i = 0; i < n; ++i) {
+        int k0 = 3 * (i / 3);
+        ld sacc = c[i];
+        for (int j = k0; j < k0 + 3; ++j) sacc += Z[(size_t)i * n + j] * y[j];
+        u[i] = sacc;
+      }
+      for (int i = 0; i < n; ++i) {
+        ld sacc = gs[i];
+        for (int j = 0; j < n; ++j) sacc += Hs[(size_t)i * n + j] * u[j];
+        r[i] = -sacc;
+      }
+      bool pv = false;
+      for (int k = 0; k < K; ++k) {
+        ld fx = u[3 * k], fy = u[3 * k + 1], fz = u[3 * k + 2];
+        if (zz[k] == 0 && (fz > dmax + tol || fz < dmin - tol)) pv = true;
+        bool xfree = (zx[k] == 0) && !(zz[k] == -1 && dmin == 0), yfree = (zy[k] == 0) && !(zz[k] == -1 && dmin == 0);
+        if ((xfree && fabsl(fx) > mu_f * fz + tol) || (yfree && fabsl(fy) > mu_f * fz + tol)) pv = true;
+      }
+      int changed = 0;
+      for (int k = 0; k < K; ++k) {
+        ld fx = u[3 * k], fy = u[3 * k + 1], fz = u[3 * k + 2];
+        ld rx = r[3 * k], ry = r[3 * k + 1], rz = r[3 * k + 2];
+        if (zz[k] == -1 && dmin == 0) {
+          if (!pv && -rz / mu_f < fabsl(rx) + fabsl(ry) - tol) {
+            zz[k] = 0;
+            zx[k] = fabsl(rx) > tol ? (rx > 0 ? 1 : -1) : 0;
+            zy[k] = fabsl(ry) > tol ? (ry > 0 ? 1 : -1) : 0;
+            changed++;
+          }
+          continue;
+        }
+        ld lx = zx[k] ? zx[k] * rx : 0.0L, ly = zy[k] ? zy[k] * ry : 0.0L;
+        ld l5 = rz + mu_f * (lx + ly);  // multiplier of fz<=max (if >0) or of fz>=min (if <0)
+        int nzx = zx[k], nzy = zy[k], nzz = zz[k];
+        if (!pv) {
+          if (zx[k] && lx < -tol) nzx = 0;
+          if (zy[k] && ly < -tol) nzy = 0;
+          if (zz[k] == 1 && l5 < -tol) nzz = 0;
+          if (zz[k] == -1 && l5 > tol) nzz = 0;
+        }
+        if (zz[k] == 0) {
+          if (fz > dmax + tol) nzz = 1;
+          else if (fz < dmin - tol) nzz = -1;
+        }
+        if (!(nzz == -1 && dmin == 0)) {
+          if (zx[k] == 0 && fabsl(fx) > mu_f * fz + tol) nzx = fx > 0 ? 1 : -1;
+          if (zy[k] == 0 && fabsl(fy) > mu_f * fz + tol) nzy = fy > 0 ? 1 : -1;
+        }
+        if (nzx != zx[k] || nzy != zy[k] || nzz != zz[k]) {
+          changed++;
+          zx[k] = nzx; zy[k] = nzy; zz[k] = nzz;
+          if (nzz == -1 && dmin == 0) zx[k] = zy[k] = 0;
+        }
+      }
+      if (changed == 0) {
+        for (int i = 0; i < n; ++i) u_out[i] = u[i] * fs;
+        return true;
+      }
+    }
+    return false;
+  };
+
+  ld mu_target = 1e-10L;
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    bool ipm_ok = false;
+    for (; info->ipm_iters < 80;) {
+      // residuals
+      ld mu = 0, rdmax = 0, rpmax = 0;
+      for (int i = 0; i < n; ++i) {
+        ld sacc = gs[i];
+        for (int j = 0; j < n; ++j) sacc += Hs[(size_t)i * n + j] * x[j];
+        rd[i] = sacc;
+      }
+      for (int k = 0; k < K; ++k)
+        for (int r = 0; r < 6; ++r) {
+          ld c3[3];
+          Crow(r, c3);
+          int i = 6 * k + r;
+          for (int a = 0; a < 3; ++a) rd[3 * k + a] += c3[a] * lam[i];
+          rp[i] = c3[0] * x[3 * k] + c3[1] * x[3 * k + 1] + c3[2] * x[3 * k + 2] + s[i] - dval(r);
+          mu += s[i] * lam[i];
+          rpmax = std::max(rpmax, fabsl(rp[i]));
+        }
+      mu /= m;
+      for (int i = 0; i < n; ++i) rdmax = std::max(rdmax, fabsl(rd[i]));
+      if (mu < mu_target && rdmax < 1e-9L && rpmax < 1e-9L) { ipm_ok = true; break; }
+      for (int i = 0; i < m; ++i) w[i] = lam[i] / s[i];
+      Kmat = Hs;
+      for (int k = 0; k < K; ++k)
+        for (int r = 0; r < 6; ++r) {
+          ld c3[3];
+          Crow(r, c3);
+          for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) Kmat[(size_t)(3 * k + a) * n + 3 * k + b] += w[6 * k + r] * c3[a] * c3[b];
+        }
+      if (!ld_chol(Kmat, n)) break;
+      auto solve = [&](const std::vector<ld>& rc_, std::vector<ld>& dx_, std::vector<ld>& ds_, std::vector<ld>& dl_) {
+        for (int i = 0; i < n; ++i) rhs[i] = -rd[i];
+        for (int k = 0; k < K; ++k)
+          for (int r = 0; r < 6; ++r) {
+            ld c3[3];
+            Crow(r, c3);
+            int i = 6 * k + r;
+            ld t = rc_[i] / s[i] - w[i] * rp[i];
+            for (int a = 0; a < 3; ++a) rhs[3 * k + a] += c3[a] * t;
+          }
+        ld_chol_solve(Kmat, n, rhs.data());
+        dx_ = rhs;
+        for (int k = 0; k < K; ++k)
+          for (int r = 0; r < 6; ++r) {
+            ld c3[3];
+            Crow(r, c3);
+            int i = 6 * k + r;
+            ds_[i] = -rp[i] - (c3[0] * dx_[3 * k] + c3[1] * dx_[3 * k + 1] + c3[2] * dx_[3 * k + 2]);
+            dl_[i] = -(rc_[i] + lam[i] * ds_[i]) / s[i];
+          }
+      };
+      for (int i = 0; i < m; ++i) rc[i] = s[i] * lam[i];
+      solve(rc, dxa, dsa, dla);
+      ld aa = std::min(amax(s, dsa), amax(lam, dla));
+      ld mu_aff = 0;
+      for (int i = 0; i < m; ++i) mu_aff += (s[i] + aa * dsa[i]) * (lam[i] + aa * dla[i]);
+      mu_aff /= m;
+      ld sigma = powl(mu_aff / mu, 3);
+      for (int i = 0; i < m; ++i) rc[i] = s[i] * lam[i] + dsa[i] * dla[i] - sigma * mu;
+      solve(rc, dx, ds, dl);
+      ld ap = amax(s, ds), ad = amax(lam, dl);
+      ld a = std::min(ap < 1 ? 0.995L * ap : 1.0L, ad < 1 ? 0.995L * ad : 1.0L);
+      for (int i = 0; i < n; ++i) x[i] += a * dx[i];
+      for (int i = 0; i < m; ++i) { s[i] += a * ds[i]; lam[i] += a * dl[i]; }
+      info->ipm_iters++;
+    }
+    // guess faces from the iterate
+    for (int k = 0; k < K; ++k) {
+      bool act[6];
+      for (int r = 0; r < 6; ++r) act[r] = lam[6 * k + r] > s[6 * k + r];
+      zx[k] = zy[k] = zz[k] = 0;
+      if (dmin == 0 && ((act[0] && act[1]) || (act[2] && act[3]) || act[5])) { zz[k] = -1; continue; }
+      zx[k] = act[0] ? -1 : (act[1] ? 1 : 0);
+      zy[k] = act[2] ? -1 : (act[3] ? 1 : 0);
+      zz[k] = act[4] ? 1 : (act[5] ? -1 : 0);
+    }
+    if (finisher(6)) { info->verified = 1; return true; }
+    if (!ipm_ok) break;
+    mu_target *= 1e-3L;
+  }
+  for (int i = 0; i < n; ++i) u_out[i] = x[i] * fs;
+  info->verified = 0;
+  return false;
+}
+
+// KKT certificate on the literal problem: given x, find multipliers y per foot-step in closed form
+// and report stationarity / feasibility residuals (all in the problem's own units).
+static void kkt_certificate(int N, const Mat& P, const double* q, const double* lbv, const double* ubv, double mu_f,
+                            const std::vector<ld>& x, ExactInfo* info) {
+  const int n = 12 * N;
+  ld stat = 0, prim = 0, dual = 0;
+  std::vector<ld> r(n);
+  for (int i = 0; i < n; ++i) {
+    ld s = q[i];
+    for (int j = 0; j < n; ++j) s += (ld)P(i, j) * x[j];
+    r[i] = -s;  // must equal A' y
+  }
+  for (int k = 0; k < 4 * N; ++k) {
+    ld fx = x[3 * k], fy = x[3 * k + 1], fz = x[3 * k + 2];
+    ld rx = r[3 * k], ry = r[3 * k + 1], rz = r[3 * k + 2];
+    ld lo5 = lbv[5 * k + 4], up5 = ubv[5 * k + 4];
+    // primal feasibility of the 5 rows
+    prim = std::max(prim, -(fx + mu_f * fz));
+    prim = std::max(prim, (fx - mu_f * fz));
+    prim = std::max(prim, -(fy + mu_f * fz));
+    prim = std::max(prim, (fy - mu_f * fz));
+    prim = std::max(prim, lo5 - fz);
+    prim = std::max(prim, fz - up5);
+    const ld tolact = 1e-9L;
+    // rows: y0 <= 0 on fx+mu fz >= 0 ; y1 >= 0 on fx-mu fz <= 0 ; y2, y3 likewise ; y4 on lo<=fz<=up
+    // stationarity: rx = y0 + y1 ; ry = y2 + y3 ; rz = mu(y0 - y1 + y2 - y3) + y4
+    bool a0 = fabsl(fx + mu_f * fz) <= tolact, a1 = fabsl(fx - mu_f * fz) <= tolact;
+    bool a2 = fabsl(fy + mu_f * fz) <= tolact, a3 = fabsl(fy - mu_f * fz) <= tolact;
+    bool alo = fabsl(fz - lo5) <= tolact, aup = fabsl(fz - up5) <= tolact;
+    ld y0 = 0, y1 = 0, y2 = 0, y3 = 0;
+    // x pair
+    if (a0 && a1) { y0 = std::min(rx, (ld)0); y1 = std::max(rx, (ld)0); }
+    else if (a0) y0 = rx; else if (a1) y1 = rx;
+    if (a2 && a3) { y2 = std::min(ry, (ld)0); y3 = std::max(ry, (ld)0); }
+    else if (a2) y2 = ry; else if (a3) y3 = ry;
+    stat = std::max(stat, fabsl(rx - y0 - y1));
+    stat = std::max(stat, fabsl(ry - y2 - y3));
+    dual = std::max(dual, y0);    // y0 must be <= 0
+    dual = std::max(dual, -y1);   // y1 >= 0
+    dual = std::max(dual, y2);
+    dual = std::max(dual, -y3);
+    ld y4 = rz - mu_f * (y0 - y1 + y2 - y3);
+    // at the vertex fx=fy=fz=0 the pairs (y0,y1), (y2,y3) are determined only up to a common shift t>=0 that
+    // RAISES y4 by 2 mu t; the smallest y4 (t=0, computed above) is the one to test at a lower bound.
+    if (alo && aup) { /* equality row: free sign */ }
+    else if (alo) dual = std::max(dual, y4);       // need y4 <= 0
+    else if (aup) dual = std::max(dual, -y4);      // need y4 >= 0
+    else stat = std::max(stat, fabsl(y4));         // inactive: must vanish
+  }
+  info->kkt_stat = (double)stat;
+  info->kkt_prim = (double)std::max(prim, (ld)0);
+  info->kkt_dual = (double)std::max(dual, (ld)0);
+}
+
+// exact solve of the literal MPC QP (P 12N x 12N, q, pyramid constraints with contact pattern)
+static bool exact_solve_literal(int N, const Mat& P, const double* q, const double* lbv, const double* ubv,
+                                const bool* contacts, double mu_f, double fzmin, double fzmax, double* x_out,
+                                ExactInfo* info) {
+  const int nfull = 12 * N;
+  std::vector<int> idx;
+  for (int k = 0; k < N; ++k)
+    for (int i = 0; i < 4; ++i)
+      if (contacts[i])
+        for (int a = 0; a < 3; ++a) idx.push_back(12 * k + 3 * i + a);
+  const int n = (int)idx.size();
+  std::vector<ld> xfull(nfull, 0.0L);
+  bool ok = true;
+  if (n > 0) {
+    std::vector<ld> H((size_t)n * n), g(n), u(n);
+    for (int i = 0; i < n; ++i) {
+      g[i] = q[idx[i]];
+      for (int j = 0; j < n; ++j) H[(size_t)i * n + j] = P(idx[i], idx[j]);
+    }
+    ok = exact_reduced(n, H, g, mu_f, fzmin, fzmax, u, info);
+    for (int i = 0; i < n; ++i) xfull[idx[i]] = u[i];
+  } else {
+    info->verified = 1;
+  }
+  kkt_certificate(N, P, q, lbv, ubv, mu_f, xfull, info);
+  for (int i = 0; i < nfull; ++i) x_out[i] = (double)xfull[i];
+  return ok;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C entry points (loaded with ctypes by tests/ and bench.py only)
+// ==========================================================================================
+extern "C" {
+
+enum { ORACLE_MODE_EXACT = 0, ORACLE_MODE_OSQP_DEFAULT = 1, ORACLE_MODE_OSQP_TIGHT = 2, ORACLE_MODE_BUILD_ONLY = 3 };
+
+// ConvexMpc members after compute_grf drove it, for QP `b` of the batch.  Any output may be NULL.
+int oracle_build_qp(const a1mpc_config* cfg, const a1mpc_inputs* in, int b, double* H, double* g, double* A,
+                    double* lb, double* ub) {
+  const int N = cfg->horizon;
+  RobotState st;
+  unpack(in, b, &st);
+  ConvexMpcRestated mpc(N, cfg->q, cfg->r, cfg->mu, cfg->fz_min, cfg->fz_max);
+  std::vector<double> x0, xd;
+  drive_convex_mpc(mpc, *cfg, st, x0, xd);
+  const int n = 12 * N, m = 20 * N;
+  if (H) std::memcpy(H, mpc.hessian.a.data(), sizeof(double) * n * n);
+  if (g) std::memcpy(g, mpc.gradient.data(), sizeof(double) * n);
+  if (A) std::memcpy(A, mpc.linear_constraints.a.data(), sizeof(double) * m * n);
+  if (lb) std::memcpy(lb, mpc.lb.data(), sizeof(double) * m);
+  if (ub) std::memcpy(ub, mpc.ub.data(), sizeof(double) * m);
+  return 0;
+}
+
+// general ConvexMpc::calculate_qp_mats with caller-supplied A_d, B_d_list (test_mpc.cpp:106-125)
+int oracle_qp_mats(const a1mpc_config* cfg, const double* A_d, const double* B_d_list, const double* x0,
+                   const double* x_d, double* H, double* g) {
+  const int N = cfg->horizon;
+  ConvexMpcRestated mpc(N, cfg->q, cfg->r, cfg->mu, cfg->fz_min, cfg->fz_max);
+  for (int i = 0; i < 13; ++i)
+    for (int j = 0; j < 13; ++j) mpc.A_mat_d(i, j) = A_d[13 * i + j];
+  for (int i = 0; i < 13 * N; ++i)
+    for (int j = 0; j < 12; ++j) mpc.B_mat_d_list(i, j) = B_d_list[12 * i + j];
+  bool contacts[4] = {true, true, true, true};
+  mpc.calculate_qp_mats(x0, x_d, contacts);
+  const int n = 12 * N;
+  if (H) std::memcpy(H, mpc.hessian.a.data(), sizeof(double) * n * n);
+  if (g) std::memcpy(g, mpc.gradient.data(), sizeof(double) * n);
+  return 0;
+}
+
+// info[8]: iters, status/verified, kkt_stat, kkt_prim, kkt_dual, rounds, pri_res, dua_res
+static int solve_one(const a1mpc_config* cfg, const a1mpc_inputs* in, int b, int mode, double eps, double* f_body,
+                     double* u_full, double* info8) {
+  const int N = cfg->horizon;
+  const int n = 12 * N, m = 20 * N;
+  RobotState st;
+  unpack(in, b, &st);
+  ConvexMpcRestated mpc(N, cfg->q, cfg->r, cfg->mu, cfg->fz_min, cfg->fz_max);
+  std::vector<double> x0, xd, sol(n, 0.0);
+  drive_convex_mpc(mpc, *cfg, st, x0, xd);
+  if (info8) std::fill(info8, info8 + 8, 0.0);
+  if (mode == ORACLE_MODE_EXACT) {
+    ExactInfo ei;
+    exact_solve_literal(N, mpc.hessian, mpc.gradient.data(), mpc.lb.data(), mpc.ub.data(), st.contacts, cfg->mu,
+                        cfg->fz_min, cfg->fz_max, sol.data(), &ei);
+    if (info8) {
+      info8[0] = ei.ipm_iters; info8[1] = ei.verified; info8[2] = ei.kkt_stat; info8[3] = ei.kkt_prim;
+      info8[4] = ei.kkt_dual; info8[5] = ei.rounds;
+    }
+  } else if (mode == ORACLE_MODE_OSQP_DEFAULT || mode == ORACLE_MODE_OSQP_TIGHT) {
+    OsqpSettings os;
+    if (mode == ORACLE_MODE_OSQP_TIGHT) { os.eps_abs = os.eps_rel = (eps > 0 ? eps : 1e-11); os.max_iter = 400000; }
+    SparseRows A;
+    A.from_dense(mpc.linear_constraints);
+    OsqpInfo oi;
+    osqp_restated_solve(n, m, mpc.hessian, mpc.gradient.data(), A, mpc.lb.data(), mpc.ub.data(), os, sol.data(), &oi);
+    if (info8) { info8[0] = oi.iter; info8[1] = oi.status; info8[5] = oi.rho_updates; info8[6] = oi.pri_res; info8[7] = oi.dua_res; }
+  }
+  // A1RobotControl.cpp:555-561: f_body = R^T * solution[3i:3i+3]
+  if (f_body)
+    for (int i = 0; i < 4; ++i)
+      for (int a = 0; a < 3; ++a)
+        f_body[3 * i + a] = st.R[0 * 3 + a] * sol[3 * i] + st.R[1 * 3 + a] * sol[3 * i + 1] + st.R[2 * 3 + a] * sol[3 * i + 2];
+  if (u_full) std::memcpy(u_full, sol.data(), sizeof(double) * n);
+  return 0;
+}
+
+// Batched compute_grf (MPC branch) on `nthreads` host threads, one QP per task.
+// f_body [12][B] SoA (ld = B), u_full [B][12N] QP-major or NULL, info [B][8] or NULL.
+int oracle_compute_grf_batch(const a1mpc_config* cfg, int B, const a1mpc_inputs* in, int mode, double eps,
+                             int nthreads, double* f_body, double* u_full, double* info) {
+  if (nthreads < 1) nthreads = 1;
+  const int n = 12 * cfg->horizon;
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    for (;;) {
+      int b = next.fetch_add(1);
+      if (b >= B) break;
+      double f[12];
+      solve_one(cfg, in, b, mode, eps, f, u_full ? u_full + (size_t)b * n : nullptr, info ? info + (size_t)b * 8 : nullptr);
+      if (f_body)
+        for (int k = 0; k < 12; ++k) f_body[(size_t)k * B + b] = f[k];
+    }
+  };
+  if (nthreads == 1) { work(); return 0; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t) th.emplace_back(work);
+  for (auto& t : th) t.join();
+  return 0;
+}
+
+// Solve a caller-supplied literal MPC QP (H 12N x 12N row-major, g) with contact pattern.
+int oracle_solve_dense(const a1mpc_config* cfg, const double* H, const double* g, uint32_t contact, int mode,
+                       double* u, double* info8) {
+  const int N = cfg->horizon, n = 12 * N, m = 20 * N;
+  ConvexMpcRestated mpc(N, cfg->q, cfg->r, cfg->mu, cfg->fz_min, cfg->fz_max);
+  std::memcpy(mpc.hessian.a.data(), H, sizeof(double) * n * n);
+  bool contacts[4];
+  for (int i = 0; i < 4; ++i) contacts[i] = (contact >> i) & 1u;
+  // bounds as ConvexMpc.cpp:223-245
+  for (int k = 0; k < 4 * N; ++k) {
+    double c = contacts[k % 4] ? 1.0 : 0.0;
+    mpc.lb[5 * k + 0] = 0; mpc.ub[5 * k + 0] = OSQP_INFTY;
+    mpc.lb[5 * k + 1] = -OSQP_INFTY; mpc.ub[5 * k + 1] = 0;
+    mpc.lb[5 * k + 2] = 0; mpc.ub[5 * k + 2] = OSQP_INFTY;
+    mpc.lb[5 * k + 3] = -OSQP_INFTY; mpc.ub[5 * k + 3] = 0;
+    mpc.lb[5 * k + 4] = cfg->fz_min * c; mpc.ub[5 * k + 4] = cfg->fz_max * c;
+  }
+  if (info8) std::fill(info8, info8 + 8, 0.0);
+  if (mode == ORACLE_MODE_EXACT) {
+    ExactInfo ei;
+    exact_solve_literal(N, mpc.hessian, g, mpc.lb.data(), mpc.ub.data(), contacts, cfg->mu, cfg->fz_min, cfg->fz_max, u, &ei);
+    if (info8) { info8[0] = ei.ipm_iters; info8[1] = ei.verified; info8[2] = ei.kkt_stat; info8[3] = ei.kkt_prim; info8[4] = ei.kkt_dual; info8[5] = ei.rounds; }
+  } else {
+    OsqpSettings os;
+    if (mode == ORACLE_MODE_OSQP_TIGHT) { os.eps_abs = os.eps_rel = 1e-11; os.max_iter = 400000; }
+    SparseRows A;
+    A.from_dense(mpc.linear_constraints);
+    OsqpInfo oi;
+    osqp_restated_solve(n, m, mpc.hessian, g, A, mpc.lb.data(), mpc.ub.data(), os, u, &oi);
+    if (info8) { info8[0] = oi.iter; info8[1] = oi.status; }
+  }
+  return 0;
+}
+
+// compute_grf's QP branch (A1RobotControl.cpp:11-48, 377-445): 12 variables, 20 rows.
+// root_acc[6], rot_z[9], rot[9] row-major, foot[12] leg-major, contact mask.  mode as above.
+int oracle_grf_qp_single(const double* root_acc, const double* rot_z, const double* rot, const double* foot,
+                         uint32_t contact, int mode, double* f_body, double* info8) {
+  const double Qd[6] = {1.0, 1.0, 1.0, 400.0, 400.0, 100.0};
+  const double Rw = 1e-3, mu = 0.7, F_min = 0, F_max = 180;
+  // inertia_inv 6x12 (:394-399)
+  double Minv[6][12];
+  double RzT[9];
+  mat3_T(rot_z, RzT);
+  for (int i = 0; i < 4; ++i) {
+    double S[9], M3[9];
+    skew(&foot[3 * i], S);
+    mat3_mul(RzT, S, M3);
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) {
+        Minv[a][3 * i + b] = (a == b) ? 1.0 : 0.0;
+        Minv[3 + a][3 * i + b] = M3[3 * a + b];
+      }
+  }
+  Mat P(12, 12);
+  double q[12];
+  for (int i = 0; i < 12; ++i) {
+    for (int j = 0; j < 12; ++j) {
+      double s = (i == j) ? Rw : 0.0;
+      for (int k = 0; k < 6; ++k) s += Minv[k][i] * Qd[k] * Minv[k][j];
+      P(i, j) = s;
+    }
+    double s = 0;
+    for (int k = 0; k < 6; ++k) s += Minv[k][i] * Qd[k] * root_acc[k];
+    q[i] = -s;
+  }
+  // linearMatrix (:28-48) 20 x 12, bounds
+  Mat A(20, 12);
+  double lb[20], ub[20];
+  for (int i = 0; i < 4; ++i) {
+    double c = ((contact >> i) & 1u) ? 1.0 : 0.0;
+    A(i, 2 + 3 * i) = 1; lb[i] = c * F_min; ub[i] = c * F_max;
+    A(4 + 4 * i, 3 * i) = 1;      A(4 + 4 * i, 2 + 3 * i) = -mu;
+    A(4 + 4 * i + 1, 3 * i) = -1; A(4 + 4 * i + 1, 2 + 3 * i) = -mu;
+    A(4 + 4 * i + 2, 1 + 3 * i) = 1;  A(4 + 4 * i + 2, 2 + 3 * i) = -mu;
+    A(4 + 4 * i + 3, 1 + 3 * i) = -1; A(4 + 4 * i + 3, 2 + 3 * i) = -mu;
+    for (int k = 0; k < 4; ++k) { lb[4 + 4 * i + k] = -OSQP_INFTY; ub[4 + 4 * i + k] = 0; }
+  }
+  double sol[12] = {0};
+  if (info8) std::fill(info8, info8 + 8, 0.0);
+  if (mode == ORACLE_MODE_EXACT) {
+    // same feasible set as a 1-step pyramid with contact-gated fz bounds: reuse the exact solver
+    bool contacts[4];
+    for (int i = 0; i < 4; ++i) contacts[i] = (contact >> i) & 1u;
+    double lb5[20], ub5[20];
+    for (int i = 0; i < 4; ++i) {
+      double c = contacts[i] ? 1.0 : 0.0;
+      lb5[5 * i + 0] = 0; ub5[5 * i + 0] = OSQP_INFTY; lb5[5 * i + 1] = -OSQP_INFTY; ub5[5 * i + 1] = 0;
+      lb5[5 * i + 2] = 0; ub5[5 * i + 2] = OSQP_INFTY; lb5[5 * i + 3] = -OSQP_INFTY; ub5[5 * i + 3] = 0;
+      lb5[5 * i + 4] = F_min * c; ub5[5 * i + 4] = F_max * c;
+    }
+    ExactInfo ei;
+    exact_solve_literal(1, P, q, lb5, ub5, contacts, mu, F_min, F_max, sol, &ei);
+    if (info8) { info8[0] = ei.ipm_iters; info8[1] = ei.verified; info8[2] = ei.kkt_stat; info8[3] = ei.kkt_prim; info8[4] = ei.kkt_dual; info8[5] = ei.rounds; }
+  } else {
+    OsqpSettings os;
+    if (mode == ORACLE_MODE_OSQP_TIGHT) { os.eps_abs = os.eps_rel = 1e-11; os.max_iter = 400000; }
+    SparseRows As;
+    As.from_dense(A);
+    OsqpInfo oi;
+    osqp_restated_solve(12, 20, P, q, As, lb, ub, os, sol, &oi);
+    if (info8) { info8[0] = oi.iter; info8[1] = oi.status; }
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int a = 0; a < 3; ++a)
+      f_body[3 * i + a] = rot[0 * 3 + a] * sol[3 * i] + rot[1 * 3 + a] * sol[3 * i + 1] + rot[2 * 3 + a] * sol[3 * i + 2];
+  return 0;
+}
+
+// wall-clock timing of the reference-faithful path (build + OSQP default, cold start) on nthreads
+double oracle_time_reference_path(const a1mpc_config* cfg, int B, const a1mpc_inputs* in, int nthreads, double* f_body) {
+  auto t0 = std::chrono::steady_clock::now();
+  oracle_compute_grf_batch(cfg, B, in, ORACLE_MODE_OSQP_DEFAULT, 0.0, nthreads, f_body, nullptr, nullptr);
+  auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+int oracle_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
+
+}  // extern "C"

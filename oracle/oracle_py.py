@@ -1,0 +1,151 @@
+"""ctypes binding of the CPU oracle (oracle/liba1mpc_oracle.so).  TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product (a1-qp-mpc-controller_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+MODE_EXACT, MODE_OSQP_DEFAULT, MODE_OSQP_TIGHT, MODE_BUILD_ONLY = 0, 1, 2, 3
+
+
+class Config(C.Structure):
+    """mirror of a1mpc_config (include/a1mpc.h)"""
+    _fields_ = [("horizon", C.c_int), ("precision", C.c_int), ("dt", C.c_double),
+                ("mu", C.c_double), ("fz_min", C.c_double), ("fz_max", C.c_double),
+                ("mass", C.c_double), ("inertia", C.c_double * 9),
+                ("q", C.c_double * 13), ("r", C.c_double * 12),
+                ("max_iter", C.c_int), ("tol", C.c_double)]
+
+
+class Inputs(C.Structure):
+    _fields_ = [("x0", C.c_void_p), ("rot", C.c_void_p), ("foot", C.c_void_p), ("ref", C.c_void_p),
+                ("contact", C.c_void_p), ("ld", C.c_size_t)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liba1mpc_oracle.so")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, "a1mpc_oracle.cpp")):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liba1mpc_oracle.so")
+        if not os.path.exists(so):
+            build()
+        _LIB = C.CDLL(so)
+        _LIB.oracle_time_reference_path.restype = C.c_double
+    return _LIB
+
+
+def make_config(horizon=10, dt=0.0025, mu=0.3, fz_max=180.0, mass=12.0,
+                inertia=(0.0158533, 0, 0, 0, 0.0377999, 0, 0, 0, 0.0456542),
+                q=(20, 10, 1, 0, 0, 420, .05, .05, .05, 30, 30, 10, 0), r=(1e-7,) * 12):
+    c = Config()
+    c.horizon, c.precision, c.dt, c.mu, c.fz_min, c.fz_max, c.mass = horizon, 64, dt, mu, 0.0, fz_max, mass
+    c.inertia[:] = inertia
+    c.q[:] = q
+    c.r[:] = r
+    c.max_iter, c.tol = 0, 0.0
+    return c
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Batch:
+    """host SoA batch: x0[12,B], rot[9,B], foot[12,B], ref[9,B], contact[B]"""
+
+    def __init__(self, x0, rot, foot, ref, contact):
+        self.x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        self.rot = np.ascontiguousarray(rot, dtype=np.float64)
+        self.foot = np.ascontiguousarray(foot, dtype=np.float64)
+        self.ref = np.ascontiguousarray(ref, dtype=np.float64)
+        self.contact = np.ascontiguousarray(contact, dtype=np.uint32)
+        self.B = self.x0.shape[1]
+        assert self.x0.shape == (12, self.B) and self.rot.shape == (9, self.B)
+        assert self.foot.shape == (12, self.B) and self.ref.shape == (9, self.B) and self.contact.shape == (self.B,)
+
+    def c_inputs(self):
+        s = Inputs()
+        s.x0, s.rot, s.foot, s.ref, s.contact, s.ld = _ptr(self.x0), _ptr(self.rot), _ptr(self.foot), _ptr(self.ref), _ptr(self.contact), self.B
+        return s
+
+    def slice(self, lo, hi):
+        return Batch(self.x0[:, lo:hi], self.rot[:, lo:hi], self.foot[:, lo:hi], self.ref[:, lo:hi], self.contact[lo:hi])
+
+
+def build_qp(cfg, batch, b):
+    N = cfg.horizon
+    n, m = 12 * N, 20 * N
+    H = np.zeros((n, n)); g = np.zeros(n); A = np.zeros((m, n)); lb = np.zeros(m); ub = np.zeros(m)
+    inp = batch.c_inputs()
+    lib().oracle_build_qp(C.byref(cfg), C.byref(inp), b, _ptr(H), _ptr(g), _ptr(A), _ptr(lb), _ptr(ub))
+    return H, g, A, lb, ub
+
+
+def qp_mats(cfg, A_d, B_d_list, x0, x_d):
+    n = 12 * cfg.horizon
+    H = np.zeros((n, n)); g = np.zeros(n)
+    A_d = np.ascontiguousarray(A_d, dtype=np.float64); B_d_list = np.ascontiguousarray(B_d_list, dtype=np.float64)
+    x0 = np.ascontiguousarray(x0, dtype=np.float64); x_d = np.ascontiguousarray(x_d, dtype=np.float64)
+    lib().oracle_qp_mats(C.byref(cfg), _ptr(A_d), _ptr(B_d_list), _ptr(x0), _ptr(x_d), _ptr(H), _ptr(g))
+    return H, g
+
+
+def compute_grf_batch(cfg, batch, mode=MODE_EXACT, eps=0.0, nthreads=1, want_u=False):
+    """returns f_body [12,B], info [B,8] (, u_full [B,12N])"""
+    B = batch.B
+    f = np.zeros((12, B)); info = np.zeros((B, 8))
+    u = np.zeros((B, 12 * cfg.horizon)) if want_u else None
+    inp = batch.c_inputs()
+    lib().oracle_compute_grf_batch(C.byref(cfg), B, C.byref(inp), mode, C.c_double(eps), nthreads, _ptr(f),
+                                   _ptr(u) if want_u else None, _ptr(info))
+    return (f, info, u) if want_u else (f, info)
+
+
+def solve_dense(cfg, H, g, contact, mode=MODE_EXACT):
+    n = 12 * cfg.horizon
+    u = np.zeros(n); info = np.zeros(8)
+    H = np.ascontiguousarray(H, dtype=np.float64); g = np.ascontiguousarray(g, dtype=np.float64)
+    lib().oracle_solve_dense(C.byref(cfg), _ptr(H), _ptr(g), C.c_uint32(int(contact)), mode, _ptr(u), _ptr(info))
+    return u, info
+
+
+def grf_qp_single(root_acc, rot_z, rot, foot, contact, mode=MODE_EXACT):
+    f = np.zeros(12); info = np.zeros(8)
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (root_acc, rot_z, rot, foot)]
+    lib().oracle_grf_qp_single(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), C.c_uint32(int(contact)), mode, _ptr(f), _ptr(info))
+    return f, info
+
+
+def time_reference_path(cfg, batch, nthreads):
+    f = np.zeros((12, batch.B))
+    inp = batch.c_inputs()
+    sec = lib().oracle_time_reference_path(C.byref(cfg), batch.B, C.byref(inp), nthreads, _ptr(f))
+    return sec, f
+
+
+def hardware_threads():
+    return int(lib().oracle_hardware_threads())
+
+
+def test_mpc_fixture():
+    """The hand-built state of the reference's only standalone driver (test/test_mpc.cpp:15-91)."""
+    cfg = make_config(horizon=10, mass=15.0, q=(1, 1, 1, 0, 0, 50, 0, 0, 1, 1, 1, 1, 0), r=(1e-6,) * 12)
+    x0 = np.zeros((12, 1)); x0[5, 0] = 0.15
+    rot = np.eye(3).reshape(9, 1)
+    foot = np.array([[.17, .15, -.35], [.17, -.15, -.35], [-.17, .15, -.35], [-.17, -.15, -.35]]).reshape(12, 1)
+    ref = np.zeros((9, 1)); ref[8, 0] = 0.15
+    contact = np.array([0b0101], dtype=np.uint32)  # FL and RL (contacts[0], contacts[2])
+    return cfg, Batch(x0, rot, foot, ref, contact)
