@@ -1,0 +1,273 @@
+"""ctypes binding of liba1mpc.so (the C ABI in include/a1mpc.h).
+
+This file is glue for tests/ and bench.py: it marshals numpy arrays to the C entry points and nothing
+else.  There is no Python compute path and no fallback: if the shared library is missing or no B200 is
+visible, construction fails loudly.  C++ hosts use include/a1mpc.h (or the ConvexMpcBatch /
+A1RobotControlBatch shims under host/) directly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liba1mpc.so")
+
+STATUS_OPTIMAL, STATUS_IPM_ONLY, STATUS_MAXITER, STATUS_NUMERICAL, STATUS_NO_CONTACT = 0, 1, 2, 3, 4
+
+EXPORTS = [
+    "a1mpc_default_config", "a1mpc_create", "a1mpc_destroy", "a1mpc_last_error", "a1mpc_device_count",
+    "a1mpc_solve_batch", "a1mpc_build_qp_batch", "a1mpc_qp_mats_batch", "a1mpc_solve_dense_batch",
+    "a1mpc_grf_qp_batch", "a1mpc_device_alloc", "a1mpc_device_free", "a1mpc_host_alloc", "a1mpc_host_free",
+    "a1mpc_memcpy_h2d", "a1mpc_memcpy_d2h", "a1mpc_sync", "a1mpc_event_create", "a1mpc_event_destroy",
+    "a1mpc_event_record", "a1mpc_event_elapsed_ms", "a1mpc_launch_count", "a1mpc_measure_fp64_peak",
+    "a1mpc_flush_l2", "a1mpc_nccl_unique_id", "a1mpc_nccl_init", "a1mpc_allgather_forces", "a1mpc_gen_states",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("horizon", C.c_int), ("precision", C.c_int), ("dt", C.c_double),
+                ("mu", C.c_double), ("fz_min", C.c_double), ("fz_max", C.c_double),
+                ("mass", C.c_double), ("inertia", C.c_double * 9),
+                ("q", C.c_double * 13), ("r", C.c_double * 12),
+                ("max_iter", C.c_int), ("tol", C.c_double)]
+
+
+class Inputs(C.Structure):
+    _fields_ = [("x0", C.c_void_p), ("rot", C.c_void_p), ("foot", C.c_void_p), ("ref", C.c_void_p),
+                ("contact", C.c_void_p), ("ld", C.c_size_t)]
+
+
+class Outputs(C.Structure):
+    _fields_ = [("f_body", C.c_void_p), ("status", C.c_void_p), ("iters", C.c_void_p), ("u_full", C.c_void_p),
+                ("ld", C.c_size_t)]
+
+
+_lib = None
+
+
+def lib():
+    """loads liba1mpc.so; raises if it has not been built (python __graft_entry__.py build / make)"""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("liba1mpc.so is missing: run `make` (or __graft_entry__.build()) first; "
+                               "there is no Python/CPU fallback for the engine")
+        l = C.CDLL(LIB_PATH)
+        l.a1mpc_last_error.restype = C.c_char_p
+        l.a1mpc_launch_count.restype = C.c_int64
+        l.a1mpc_launch_count.argtypes = [C.c_void_p]
+        for name in ("a1mpc_device_alloc", "a1mpc_host_alloc"):
+            getattr(l, name).argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        for name in ("a1mpc_device_free", "a1mpc_host_free", "a1mpc_event_destroy", "a1mpc_event_record"):
+            getattr(l, name).argtypes = [C.c_void_p, C.c_void_p]
+        for name in ("a1mpc_memcpy_h2d", "a1mpc_memcpy_d2h"):
+            getattr(l, name).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        l.a1mpc_sync.argtypes = [C.c_void_p]
+        l.a1mpc_flush_l2.argtypes = [C.c_void_p]
+        l.a1mpc_destroy.argtypes = [C.c_void_p]
+        l.a1mpc_event_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        l.a1mpc_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        l.a1mpc_solve_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Inputs), C.POINTER(Outputs)]
+        l.a1mpc_build_qp_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Inputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.a1mpc_qp_mats_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
+        l.a1mpc_solve_dense_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        l.a1mpc_grf_qp_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
+        l.a1mpc_gen_states.argtypes = [C.c_int, C.c_uint64, C.c_int] + [C.c_void_p] * 5
+        l.a1mpc_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        l.a1mpc_nccl_unique_id.argtypes = [C.c_void_p]
+        l.a1mpc_nccl_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        l.a1mpc_allgather_forces.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _lib = l
+    return _lib
+
+
+class A1MpcError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc != 0:
+        raise A1MpcError("a1mpc error %d: %s" % (rc, (lib().a1mpc_last_error() or b"").decode()))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def default_config(**kw):
+    c = Config()
+    lib().a1mpc_default_config(C.byref(c))
+    for k, v in kw.items():
+        if k in ("inertia", "q", "r"):
+            getattr(c, k)[:] = v
+        else:
+            setattr(c, k, v)
+    return c
+
+
+def gen_states(B, config_id=2, stream=0):
+    """deterministic synthetic trot-gait batch -> dict of host SoA arrays"""
+    x0 = np.zeros((12, B)); rot = np.zeros((9, B)); foot = np.zeros((12, B)); ref = np.zeros((9, B))
+    contact = np.zeros(B, dtype=np.uint32)
+    rc = lib().a1mpc_gen_states(config_id, stream, B, _p(x0), _p(rot), _p(foot), _p(ref), _p(contact))
+    _check(rc)
+    return dict(x0=x0, rot=rot, foot=foot, ref=ref, contact=contact)
+
+
+class DeviceBatch:
+    """device-resident SoA inputs + outputs of one batch (ld = B)"""
+
+    def __init__(self, eng, B, want_u=False, want_iters=True):
+        self.eng, self.B = eng, B
+        N = eng.cfg.horizon
+        self.x0 = eng.dalloc(12 * B * 8); self.rot = eng.dalloc(9 * B * 8); self.foot = eng.dalloc(12 * B * 8)
+        self.ref = eng.dalloc(9 * B * 8); self.contact = eng.dalloc(B * 4)
+        self.f_body = eng.dalloc(12 * B * 8); self.status = eng.dalloc(B * 4)
+        self.iters = eng.dalloc(B * 4) if want_iters else None
+        self.u_full = eng.dalloc(12 * N * B * 8) if want_u else None
+        self.inp = Inputs(self.x0, self.rot, self.foot, self.ref, self.contact, B)
+        self.out = Outputs(self.f_body, self.status, self.iters, self.u_full, B)
+
+    def upload(self, st):
+        e = self.eng
+        for name in ("x0", "rot", "foot", "ref", "contact"):
+            a = np.ascontiguousarray(st[name])
+            _check(lib().a1mpc_memcpy_h2d(e.h, getattr(self, name), _p(a), a.nbytes))
+        e.sync()
+
+    def download(self):
+        e, B = self.eng, self.B
+        f = np.zeros((12, B)); status = np.zeros(B, dtype=np.int32)
+        _check(lib().a1mpc_memcpy_d2h(e.h, _p(f), self.f_body, f.nbytes))
+        _check(lib().a1mpc_memcpy_d2h(e.h, _p(status), self.status, status.nbytes))
+        e.sync()
+        return f, status
+
+    def free(self):
+        for name in ("x0", "rot", "foot", "ref", "contact", "f_body", "status", "iters", "u_full"):
+            p = getattr(self, name)
+            if p:
+                lib().a1mpc_device_free(self.eng.h, p)
+                setattr(self, name, None)
+
+
+class Engine:
+    """one handle = one B200 + one stream (a1mpc_create / a1mpc_destroy)"""
+
+    def __init__(self, cfg=None, device=0):
+        self.cfg = cfg if cfg is not None else default_config()
+        h = C.c_void_p()
+        _check(lib().a1mpc_create(C.byref(h), C.byref(self.cfg), device))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib().a1mpc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- hot path ----
+    def solve(self, st, want_u=False):
+        """host arrays in, host arrays out (H2D + kernels + D2H inside the call)"""
+        B = st["x0"].shape[1]
+        N = self.cfg.horizon
+        a = {k: np.ascontiguousarray(st[k], dtype=(np.uint32 if k == "contact" else np.float64)) for k in ("x0", "rot", "foot", "ref", "contact")}
+        f = np.zeros((12, B)); status = np.zeros(B, dtype=np.int32); iters = np.zeros(B, dtype=np.int32)
+        u = np.zeros((12 * N, B)) if want_u else None
+        inp = Inputs(_p(a["x0"]), _p(a["rot"]), _p(a["foot"]), _p(a["ref"]), _p(a["contact"]), B)
+        out = Outputs(_p(f), _p(status), _p(iters), _p(u), B)
+        _check(lib().a1mpc_solve_batch(self.h, B, C.byref(inp), C.byref(out)))
+        return (f, status, iters, u) if want_u else (f, status, iters)
+
+    def solve_ptrs(self, B, inp, out):
+        """raw a1mpc_solve_batch on caller-built Inputs/Outputs (host or device pointers)"""
+        _check(lib().a1mpc_solve_batch(self.h, B, C.byref(inp), C.byref(out)))
+
+    # ---- ConvexMpc parity members ----
+    def build_qp(self, st):
+        B = st["x0"].shape[1]
+        N = self.cfg.horizon
+        n, m = 12 * N, 20 * N
+        a = {k: np.ascontiguousarray(st[k], dtype=(np.uint32 if k == "contact" else np.float64)) for k in ("x0", "rot", "foot", "ref", "contact")}
+        H = np.zeros((B, n, n)); g = np.zeros((B, n)); lb = np.zeros((B, m)); ub = np.zeros((B, m))
+        inp = Inputs(_p(a["x0"]), _p(a["rot"]), _p(a["foot"]), _p(a["ref"]), _p(a["contact"]), B)
+        _check(lib().a1mpc_build_qp_batch(self.h, B, C.byref(inp), _p(H), _p(g), _p(lb), _p(ub)))
+        return H, g, lb, ub
+
+    def qp_mats(self, A_d, B_d_list, x0, x_d):
+        A_d = np.ascontiguousarray(A_d, dtype=np.float64); B_d_list = np.ascontiguousarray(B_d_list, dtype=np.float64)
+        x0 = np.ascontiguousarray(x0, dtype=np.float64); x_d = np.ascontiguousarray(x_d, dtype=np.float64)
+        B = A_d.shape[0]
+        n = 12 * self.cfg.horizon
+        H = np.zeros((B, n, n)); g = np.zeros((B, n))
+        _check(lib().a1mpc_qp_mats_batch(self.h, B, _p(A_d), _p(B_d_list), _p(x0), _p(x_d), _p(H), _p(g)))
+        return H, g
+
+    def solve_dense(self, H, g, contact):
+        H = np.ascontiguousarray(H, dtype=np.float64); g = np.ascontiguousarray(g, dtype=np.float64)
+        contact = np.ascontiguousarray(contact, dtype=np.uint32)
+        B = H.shape[0]
+        u = np.zeros((B, 12 * self.cfg.horizon)); status = np.zeros(B, dtype=np.int32)
+        _check(lib().a1mpc_solve_dense_batch(self.h, B, _p(H), _p(g), _p(contact), _p(u), _p(status)))
+        return u, status
+
+    def grf_qp(self, root_acc, rot_z, rot, foot, contact):
+        arrs = [np.ascontiguousarray(v, dtype=np.float64) for v in (root_acc, rot_z, rot, foot)]
+        contact = np.ascontiguousarray(contact, dtype=np.uint32)
+        B = arrs[0].shape[0]
+        f = np.zeros((B, 12)); status = np.zeros(B, dtype=np.int32)
+        _check(lib().a1mpc_grf_qp_batch(self.h, B, _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(contact), _p(f), _p(status)))
+        return f, status
+
+    # ---- memory / timing helpers ----
+    def dalloc(self, nbytes):
+        p = C.c_void_p()
+        _check(lib().a1mpc_device_alloc(self.h, nbytes, C.byref(p)))
+        return p
+
+    def halloc(self, nbytes):
+        p = C.c_void_p()
+        _check(lib().a1mpc_host_alloc(self.h, nbytes, C.byref(p)))
+        return p
+
+    def pinned_array(self, shape, dtype):
+        """numpy view over pinned host memory (kept alive by the returned array's base object)"""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = self.halloc(max(nbytes, 8))
+        buf = (C.c_char * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+        return arr
+
+    def sync(self):
+        _check(lib().a1mpc_sync(self.h))
+
+    def event(self):
+        e = C.c_void_p()
+        _check(lib().a1mpc_event_create(self.h, C.byref(e)))
+        return e
+
+    def record(self, ev):
+        _check(lib().a1mpc_event_record(self.h, ev))
+
+    def elapsed_ms(self, e0, e1):
+        ms = C.c_float()
+        _check(lib().a1mpc_event_elapsed_ms(self.h, e0, e1, C.byref(ms)))
+        return float(ms.value)
+
+    def launches(self):
+        return int(lib().a1mpc_launch_count(self.h))
+
+    def fp64_peak_tflops(self):
+        v = C.c_double()
+        _check(lib().a1mpc_measure_fp64_peak(self.h, C.byref(v)))
+        return float(v.value)
+
+    def flush_l2(self):
+        _check(lib().a1mpc_flush_l2(self.h))

@@ -1,0 +1,571 @@
+// a1mpc_api.cu -- C ABI of the engine (include/a1mpc.h) over the sm_100a kernels.
+// No CPU fallback anywhere in this file: every compute entry point launches CUDA kernels or fails.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <algorithm>
+
+#include "a1mpc_internal.h"
+#include "a1mpc_misc.cuh"
+
+using namespace a1mpc;
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(A1MPC_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                \
+  } while (0)
+
+}  // namespace
+
+struct a1mpc_handle {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  a1mpc_config cfg;
+  DevParams P;
+  a1mpc::ClassLaunch cls[5];  // index = number of stance feet
+  // scratch sized for `cap` QPs
+  size_t cap = 0;
+  double* d_rec = nullptr;
+  int* d_count = nullptr;
+  // device mirrors for host-pointer calls
+  double *d_x0 = nullptr, *d_rot = nullptr, *d_foot = nullptr, *d_ref = nullptr, *d_f = nullptr, *d_u = nullptr;
+  uint32_t* d_contact = nullptr;
+  int32_t *d_status = nullptr, *d_iters = nullptr;
+  size_t cap_u = 0;
+  // generic scratch for the QP-major side APIs
+  void* d_side = nullptr;
+  size_t side_bytes = 0;
+  int* d_lists = nullptr;
+  size_t lists_bytes = 0;
+  double* d_flush = nullptr;
+  size_t flush_elems = 0;
+  int64_t launches = 0;
+  // NCCL (dlopen'ed)
+  void* nccl_lib = nullptr;
+  void* nccl_comm = nullptr;
+};
+
+namespace {
+
+int ensure_capacity(a1mpc_handle* h, size_t B, bool mirrors, bool want_u) {
+  if (B > h->cap) {
+    CK(cudaStreamSynchronize(h->stream));
+    auto fr = [](void* p) { if (p) cudaFree(p); };
+    fr(h->d_rec); fr(h->d_x0); fr(h->d_rot); fr(h->d_foot); fr(h->d_ref); fr(h->d_f); fr(h->d_contact); fr(h->d_status); fr(h->d_iters);
+    fr(h->d_u);
+    h->d_rec = h->d_x0 = h->d_rot = h->d_foot = h->d_ref = h->d_f = h->d_u = nullptr;
+    h->d_contact = nullptr; h->d_status = h->d_iters = nullptr;
+    h->cap_u = 0;
+    size_t cap = 1024;
+    while (cap < B) cap *= 2;
+    h->cap = cap;
+    CK(cudaMalloc(&h->d_rec, 4 * cap * REC_BYTES));
+  }
+  if (mirrors && !h->d_x0) {
+    const size_t cap = h->cap;
+    CK(cudaMalloc(&h->d_x0, 12 * cap * 8));
+    CK(cudaMalloc(&h->d_rot, 9 * cap * 8));
+    CK(cudaMalloc(&h->d_foot, 12 * cap * 8));
+    CK(cudaMalloc(&h->d_ref, 9 * cap * 8));
+    CK(cudaMalloc(&h->d_f, 12 * cap * 8));
+    CK(cudaMalloc(&h->d_contact, cap * 4));
+    CK(cudaMalloc(&h->d_status, cap * 4));
+    CK(cudaMalloc(&h->d_iters, cap * 4));
+  }
+  if (mirrors && want_u && h->cap_u < h->cap) {
+    if (h->d_u) cudaFree(h->d_u);
+    CK(cudaMalloc(&h->d_u, (size_t)12 * h->cfg.horizon * h->cap * 8));
+    h->cap_u = h->cap;
+  }
+  return A1MPC_OK;
+}
+
+int ensure_side(a1mpc_handle* h, size_t bytes) {
+  if (bytes > h->side_bytes) {
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->d_side) cudaFree(h->d_side);
+    h->d_side = nullptr;
+    CK(cudaMalloc(&h->d_side, bytes));
+    h->side_bytes = bytes;
+  }
+  return A1MPC_OK;
+}
+
+int ensure_lists(a1mpc_handle* h, size_t bytes) {
+  if (bytes > h->lists_bytes) {
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->d_lists) cudaFree(h->d_lists);
+    h->d_lists = nullptr;
+    CK(cudaMalloc(&h->d_lists, bytes));
+    h->lists_bytes = bytes;
+  }
+  return A1MPC_OK;
+}
+
+bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// enqueue the fused path on device-resident SoA data
+int enqueue_solve(a1mpc_handle* h, int B, const DevInputs& din, const DevOutputs& dout) {
+  CK(cudaMemsetAsync(h->d_count, 0, 8 * sizeof(int), h->stream));
+  pack_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(din, B, h->d_rec, (int)h->cap, h->d_count, dout, h->cfg.horizon);
+  h->launches++;
+  CK(cudaEventRecord(h->ev_fork, h->stream));
+  const int N = h->cfg.horizon;
+  // heaviest class first, each class on its own stream so that the few long 4-stance solves overlap
+  // the many short trot solves
+  for (int ns = 4; ns >= 1; --ns) {
+    cudaStream_t st = h->side[ns - 1];
+    CK(cudaStreamWaitEvent(st, h->ev_fork, 0));
+    const double* rec = h->d_rec + (size_t)(ns - 1) * h->cap * REC_DOUBLES;
+    if (!h->cls[ns].supported) unsupported_kernel<<<(B + 127) / 128, 128, 0, st>>>(rec, h->d_count, ns, dout, N);
+    else if (N == 10) fused_launch_n10(ns, h->cls[ns], st, B, h->P, rec, h->d_count, dout);
+    else fused_launch_n20(ns, h->cls[ns], st, B, h->P, rec, h->d_count, dout);
+    h->launches++;
+    CK(cudaEventRecord(h->ev_join[ns - 1], st));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_join[ns - 1], 0));
+  }
+  CK(cudaGetLastError());
+  return A1MPC_OK;
+}
+
+int copy_rows(cudaStream_t st, void* dst, size_t dst_ld, const void* src, size_t src_ld, int rows, size_t B, size_t esz, cudaMemcpyKind kind) {
+  CK(cudaMemcpy2DAsync(dst, dst_ld * esz, src, src_ld * esz, B * esz, rows, kind, st));
+  return A1MPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* a1mpc_last_error(void) { return g_err.c_str(); }
+
+int a1mpc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+void a1mpc_default_config(a1mpc_config* c) {
+  std::memset(c, 0, sizeof(*c));
+  c->horizon = 10;
+  c->precision = 64;
+  c->dt = 0.0025;
+  c->mu = 0.3;
+  c->fz_min = 0.0;
+  c->fz_max = 180.0;
+  c->mass = 12.0;
+  c->inertia[0] = 0.0158533; c->inertia[4] = 0.0377999; c->inertia[8] = 0.0456542;
+  const double q[13] = {20, 10, 1, 0, 0, 420, 0.05, 0.05, 0.05, 30, 30, 10, 0};
+  for (int i = 0; i < 13; ++i) c->q[i] = q[i];
+  for (int i = 0; i < 12; ++i) c->r[i] = 1e-7;
+  c->max_iter = 0;
+  c->tol = 0.0;
+}
+
+int a1mpc_create(a1mpc_handle** out, const a1mpc_config* cfg, int device) {
+  if (!out || !cfg) return fail(A1MPC_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->horizon != 10 && cfg->horizon != 20) return fail(A1MPC_EINVAL, "horizon must be 10 or 20");
+  if (cfg->precision != 64) return fail(A1MPC_EINVAL, "precision must be 64 (fp32 is not implemented; see DESIGN.md)");
+  if (!(cfg->fz_min == 0.0)) return fail(A1MPC_EINVAL, "fz_min must be 0 (the reference hard-codes it, ConvexMpc.cpp:223)");
+  if (!(cfg->mu > 0.0) || !(cfg->fz_max > 0.0) || !(cfg->mass > 0.0) || !(cfg->dt > 0.0)) return fail(A1MPC_EINVAL, "mu, fz_max, mass, dt must be positive");
+  for (int i = 0; i < 12; ++i)
+    if (!(cfg->r[i] > 0.0)) return fail(A1MPC_EINVAL, "r weights must be positive (H must be positive definite)");
+  for (int i = 0; i < 13; ++i)
+    if (!(cfg->q[i] >= 0.0)) return fail(A1MPC_EINVAL, "q weights must be non-negative");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return fail(A1MPC_ENODEVICE, "no CUDA device available (this engine has no CPU fallback)");
+  }
+  if (device < 0 || device >= ndev) return fail(A1MPC_EINVAL, "device index out of range");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(A1MPC_ENODEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + "; this library is built for sm_100a only");
+  a1mpc_handle* h = new a1mpc_handle();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->cfg = *cfg;
+  DevParams& P = h->P;
+  P.N = cfg->horizon;
+  P.max_iter = cfg->max_iter > 0 ? cfg->max_iter : 40;
+  P.dt = cfg->dt; P.mu = cfg->mu; P.fzmax = cfg->fz_max; P.mass = cfg->mass;
+  P.mu_switch = cfg->tol > 0.0 ? cfg->tol : 1e-9;
+  for (int i = 0; i < 9; ++i) P.inertia[i] = cfg->inertia[i];
+  for (int i = 0; i < 13; ++i) P.q2[i] = 2.0 * cfg->q[i];
+  for (int i = 0; i < 12; ++i) P.r2[i] = 2.0 * cfg->r[i];
+  int rc = A1MPC_OK;
+  auto bail = [&](int code) { a1mpc_destroy(h); return code; };
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(A1MPC_ECUDA, "stream create failed"));
+  for (int i = 0; i < 4; ++i) {
+    if (cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking) != cudaSuccess) return bail(fail(A1MPC_ECUDA, "stream create failed"));
+    if (cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) != cudaSuccess) return bail(fail(A1MPC_ECUDA, "event create failed"));
+  }
+  if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(fail(A1MPC_ECUDA, "event create failed"));
+  if (cudaMalloc(&h->d_count, 8 * sizeof(int)) != cudaSuccess) return bail(fail(A1MPC_ENOMEM, "cudaMalloc failed"));
+  {
+    cudaError_t e = (cfg->horizon == 10) ? fused_setup_n10(h->sm_count, h->cls) : fused_setup_n20(h->sm_count, h->cls);
+    if (e != cudaSuccess) return bail(fail(A1MPC_ECUDA, std::string("kernel setup: ") + cudaGetErrorString(e)));
+    e = dense_setup(cfg->horizon);
+    if (e != cudaSuccess) return bail(fail(A1MPC_ECUDA, std::string("dense kernel setup: ") + cudaGetErrorString(e)));
+  }
+  (void)rc;
+  *out = h;
+  return A1MPC_OK;
+}
+
+int a1mpc_destroy(a1mpc_handle* h) {
+  if (!h) return A1MPC_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  auto fr = [](void* p) { if (p) cudaFree(p); };
+  fr(h->d_rec); fr(h->d_count); fr(h->d_x0); fr(h->d_rot); fr(h->d_foot); fr(h->d_ref); fr(h->d_f); fr(h->d_u);
+  fr(h->d_contact); fr(h->d_status); fr(h->d_iters); fr(h->d_side); fr(h->d_flush); fr(h->d_lists);
+  for (int i = 0; i < 4; ++i) {
+    if (h->side[i]) cudaStreamDestroy(h->side[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return A1MPC_OK;
+}
+
+int a1mpc_solve_batch(a1mpc_handle* h, int B, const a1mpc_inputs* in, const a1mpc_outputs* out) {
+  if (!h || !in || !out) return fail(A1MPC_EINVAL, "null argument");
+  if (B <= 0) return fail(A1MPC_EINVAL, "B must be positive");
+  if (!in->x0 || !in->rot || !in->foot || !in->ref || !in->contact || !out->f_body || !out->status) return fail(A1MPC_EINVAL, "null input/output array");
+  if (in->ld < (size_t)B || out->ld < (size_t)B) return fail(A1MPC_EINVAL, "ld < B");
+  CK(cudaSetDevice(h->device));
+  const bool dev_in = is_device_ptr(in->x0), dev_out = is_device_ptr(out->f_body);
+  if (dev_in != dev_out || dev_in != is_device_ptr(in->contact) || dev_in != is_device_ptr(out->status))
+    return fail(A1MPC_EINVAL, "inputs and outputs must be all-host or all-device");
+  int rc;
+  if (dev_in) {
+    if ((rc = ensure_capacity(h, B, false, false))) return rc;
+    DevInputs di{in->x0, in->rot, in->foot, in->ref, in->contact, in->ld};
+    DevOutputs dout{out->f_body, out->status, out->iters, out->u_full, out->ld};
+    return enqueue_solve(h, B, di, dout);
+  }
+  if ((rc = ensure_capacity(h, B, true, out->u_full != nullptr))) return rc;
+  const size_t Bs = (size_t)B;
+  if ((rc = copy_rows(h->stream, h->d_x0, Bs, in->x0, in->ld, 12, Bs, 8, cudaMemcpyHostToDevice))) return rc;
+  if ((rc = copy_rows(h->stream, h->d_rot, Bs, in->rot, in->ld, 9, Bs, 8, cudaMemcpyHostToDevice))) return rc;
+  if ((rc = copy_rows(h->stream, h->d_foot, Bs, in->foot, in->ld, 12, Bs, 8, cudaMemcpyHostToDevice))) return rc;
+  if ((rc = copy_rows(h->stream, h->d_ref, Bs, in->ref, in->ld, 9, Bs, 8, cudaMemcpyHostToDevice))) return rc;
+  CK(cudaMemcpyAsync(h->d_contact, in->contact, Bs * 4, cudaMemcpyHostToDevice, h->stream));
+  DevInputs di{h->d_x0, h->d_rot, h->d_foot, h->d_ref, h->d_contact, Bs};
+  DevOutputs dout{h->d_f, h->d_status, out->iters ? h->d_iters : nullptr, out->u_full ? h->d_u : nullptr, Bs};
+  if ((rc = enqueue_solve(h, B, di, dout))) return rc;
+  if ((rc = copy_rows(h->stream, out->f_body, out->ld, h->d_f, Bs, 12, Bs, 8, cudaMemcpyDeviceToHost))) return rc;
+  CK(cudaMemcpyAsync(out->status, h->d_status, Bs * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (out->iters) CK(cudaMemcpyAsync(out->iters, h->d_iters, Bs * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (out->u_full)
+    if ((rc = copy_rows(h->stream, out->u_full, out->ld, h->d_u, Bs, 12 * h->cfg.horizon, Bs, 8, cudaMemcpyDeviceToHost))) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return A1MPC_OK;
+}
+
+int a1mpc_build_qp_batch(a1mpc_handle* h, int B, const a1mpc_inputs* in, double* H, double* g, double* lb, double* ub) {
+  if (!h || !in) return fail(A1MPC_EINVAL, "null argument");
+  if (B <= 0) return fail(A1MPC_EINVAL, "B must be positive");
+  if ((lb == nullptr) != (ub == nullptr)) return fail(A1MPC_EINVAL, "lb and ub must be given together");
+  CK(cudaSetDevice(h->device));
+  const int N = h->cfg.horizon, n = 12 * N, m = 20 * N;
+  const bool dev = is_device_ptr(in->x0);
+  int rc;
+  DevInputs di{in->x0, in->rot, in->foot, in->ref, in->contact, in->ld};
+  double *dH = H, *dg = g, *dlb = lb, *dub = ub;
+  if (!dev) {
+    if ((rc = ensure_capacity(h, B, true, false))) return rc;
+    const size_t Bs = (size_t)B;
+    if ((rc = copy_rows(h->stream, h->d_x0, Bs, in->x0, in->ld, 12, Bs, 8, cudaMemcpyHostToDevice))) return rc;
+    if ((rc = copy_rows(h->stream, h->d_rot, Bs, in->rot, in->ld, 9, Bs, 8, cudaMemcpyHostToDevice))) return rc;
+    if ((rc = copy_rows(h->stream, h->d_foot, Bs, in->foot, in->ld, 12, Bs, 8, cudaMemcpyHostToDevice))) return rc;
+    if ((rc = copy_rows(h->stream, h->d_ref, Bs, in->ref, in->ld, 9, Bs, 8, cudaMemcpyHostToDevice))) return rc;
+    CK(cudaMemcpyAsync(h->d_contact, in->contact, Bs * 4, cudaMemcpyHostToDevice, h->stream));
+    di = DevInputs{h->d_x0, h->d_rot, h->d_foot, h->d_ref, h->d_contact, Bs};
+    const size_t bytes = Bs * ((size_t)n * n + n + 2 * m) * 8;
+    if ((rc = ensure_side(h, bytes))) return rc;
+    double* base = (double*)h->d_side;
+    dH = H ? base : nullptr;
+    dg = g ? base + Bs * n * n : nullptr;
+    dlb = lb ? base + Bs * n * n + Bs * n : nullptr;
+    dub = ub ? base + Bs * n * n + Bs * n + Bs * m : nullptr;
+  }
+  {
+    cudaError_t e = build_dense_launch(h->P, di, B, dH, dg, dlb, dub, h->stream);
+    if (e != cudaSuccess) return fail(A1MPC_ECUDA, std::string("build kernel: ") + cudaGetErrorString(e));
+    h->launches++;
+  }
+  if (!dev) {
+    const size_t Bs = (size_t)B;
+    if (H) CK(cudaMemcpyAsync(H, dH, Bs * n * n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (g) CK(cudaMemcpyAsync(g, dg, Bs * n * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (lb) CK(cudaMemcpyAsync(lb, dlb, Bs * m * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (ub) CK(cudaMemcpyAsync(ub, dub, Bs * m * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return A1MPC_OK;
+}
+
+int a1mpc_qp_mats_batch(a1mpc_handle* h, int B, const double* A_d, const double* B_d_list, const double* x0, const double* x_d,
+                        double* H, double* g) {
+  if (!h || !A_d || !B_d_list || !x0 || !x_d || (!H && !g)) return fail(A1MPC_EINVAL, "null argument");
+  if (B <= 0) return fail(A1MPC_EINVAL, "B must be positive");
+  CK(cudaSetDevice(h->device));
+  const int N = h->cfg.horizon, n = 12 * N;
+  const bool dev = is_device_ptr(A_d);
+  const size_t Bs = (size_t)B;
+  const size_t szA = Bs * 169, szB = Bs * 13 * N * 12, szx0 = Bs * 13, szxd = Bs * 13 * N, szH = Bs * n * n, szg = Bs * n;
+  const double *dA = A_d, *dB = B_d_list, *dx0 = x0, *dxd = x_d;
+  double *dH = H, *dg = g;
+  int rc;
+  if (!dev) {
+    if ((rc = ensure_side(h, (szA + szB + szx0 + szxd + szH + szg) * 8))) return rc;
+    double* p = (double*)h->d_side;
+    CK(cudaMemcpyAsync(p, A_d, szA * 8, cudaMemcpyHostToDevice, h->stream)); dA = p; p += szA;
+    CK(cudaMemcpyAsync(p, B_d_list, szB * 8, cudaMemcpyHostToDevice, h->stream)); dB = p; p += szB;
+    CK(cudaMemcpyAsync(p, x0, szx0 * 8, cudaMemcpyHostToDevice, h->stream)); dx0 = p; p += szx0;
+    CK(cudaMemcpyAsync(p, x_d, szxd * 8, cudaMemcpyHostToDevice, h->stream)); dxd = p; p += szxd;
+    dH = p; p += szH;
+    dg = p;
+  } else if (!H || !g) {
+    return fail(A1MPC_EINVAL, "device-pointer calls need both H and g");
+  }
+  {
+    cudaError_t e = dense_qp_mats_launch(h->P, B, dA, dB, dx0, dxd, dH, dg, h->stream);
+    if (e != cudaSuccess) return fail(A1MPC_ECUDA, std::string("qp_mats kernel: ") + cudaGetErrorString(e));
+    h->launches += 1;
+  }
+  if (!dev) {
+    if (H) CK(cudaMemcpyAsync(H, dH, szH * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (g) CK(cudaMemcpyAsync(g, dg, szg * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return A1MPC_OK;
+}
+
+int a1mpc_solve_dense_batch(a1mpc_handle* h, int B, const double* H, const double* g, const uint32_t* contact, double* u, int32_t* status) {
+  if (!h || !H || !g || !contact || !u || !status) return fail(A1MPC_EINVAL, "null argument");
+  if (B <= 0) return fail(A1MPC_EINVAL, "B must be positive");
+  CK(cudaSetDevice(h->device));
+  const int N = h->cfg.horizon, n = 12 * N;
+  const bool dev = is_device_ptr(H);
+  const size_t Bs = (size_t)B;
+  const double *dH = H, *dg = g;
+  const uint32_t* dc = contact;
+  double* du = u;
+  int32_t* ds = status;
+  int rc;
+  const size_t list_bytes = (4 * Bs + 8) * sizeof(int);
+  if ((rc = ensure_lists(h, list_bytes))) return rc;
+  if (!dev) {
+    const size_t bytes = (Bs * n * n + 2 * Bs * n) * 8 + Bs * 8;
+    if ((rc = ensure_side(h, bytes))) return rc;
+    double* p = (double*)h->d_side;
+    CK(cudaMemcpyAsync(p, H, Bs * n * n * 8, cudaMemcpyHostToDevice, h->stream)); dH = p; p += Bs * n * n;
+    CK(cudaMemcpyAsync(p, g, Bs * n * 8, cudaMemcpyHostToDevice, h->stream)); dg = p; p += Bs * n;
+    du = p; p += Bs * n;
+    uint32_t* pc = (uint32_t*)p;
+    CK(cudaMemcpyAsync(pc, contact, Bs * 4, cudaMemcpyHostToDevice, h->stream)); dc = pc;
+    ds = (int32_t*)(pc + Bs);
+  }
+  {
+    int nl = 0;
+    cudaError_t e = dense_solve_launch(h->P, h->sm_count, B, dH, dg, dc, du, ds, h->d_lists, h->stream, &nl);
+    if (e != cudaSuccess) return fail(A1MPC_ECUDA, std::string("dense solve kernels: ") + cudaGetErrorString(e));
+    h->launches += nl;
+  }
+  if (!dev) {
+    CK(cudaMemcpyAsync(u, du, Bs * n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(status, ds, Bs * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return A1MPC_OK;
+}
+
+int a1mpc_grf_qp_batch(a1mpc_handle* h, int B, const double* root_acc, const double* rot_z, const double* rot, const double* foot,
+                       const uint32_t* contact, double* f_body, int32_t* status) {
+  if (!h || !root_acc || !rot_z || !rot || !foot || !contact || !f_body || !status) return fail(A1MPC_EINVAL, "null argument");
+  if (B <= 0) return fail(A1MPC_EINVAL, "B must be positive");
+  CK(cudaSetDevice(h->device));
+  const bool dev = is_device_ptr(root_acc);
+  const size_t Bs = (size_t)B;
+  const double *da = root_acc, *drz = rot_z, *dr = rot, *dfo = foot;
+  const uint32_t* dc = contact;
+  double* df = f_body;
+  int32_t* ds = status;
+  int rc;
+  if ((rc = ensure_lists(h, (4 * Bs + 8) * sizeof(int)))) return rc;
+  if (!dev) {
+    if ((rc = ensure_side(h, Bs * (6 + 9 + 9 + 12 + 12) * 8 + Bs * 8))) return rc;
+    double* p = (double*)h->d_side;
+    CK(cudaMemcpyAsync(p, root_acc, Bs * 6 * 8, cudaMemcpyHostToDevice, h->stream)); da = p; p += Bs * 6;
+    CK(cudaMemcpyAsync(p, rot_z, Bs * 9 * 8, cudaMemcpyHostToDevice, h->stream)); drz = p; p += Bs * 9;
+    CK(cudaMemcpyAsync(p, rot, Bs * 9 * 8, cudaMemcpyHostToDevice, h->stream)); dr = p; p += Bs * 9;
+    CK(cudaMemcpyAsync(p, foot, Bs * 12 * 8, cudaMemcpyHostToDevice, h->stream)); dfo = p; p += Bs * 12;
+    df = p; p += Bs * 12;
+    uint32_t* pc = (uint32_t*)p;
+    CK(cudaMemcpyAsync(pc, contact, Bs * 4, cudaMemcpyHostToDevice, h->stream)); dc = pc;
+    ds = (int32_t*)(pc + Bs);
+  }
+  {
+    int nl = 0;
+    cudaError_t e = grf_qp_launch(h->sm_count, B, da, drz, dr, dfo, dc, df, ds, h->d_lists, h->stream, &nl);
+    if (e != cudaSuccess) return fail(A1MPC_ECUDA, std::string("grf_qp kernels: ") + cudaGetErrorString(e));
+    h->launches += nl;
+  }
+  if (!dev) {
+    CK(cudaMemcpyAsync(f_body, df, Bs * 12 * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(status, ds, Bs * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return A1MPC_OK;
+}
+
+// ---- helpers -------------------------------------------------------------------------------
+int a1mpc_device_alloc(a1mpc_handle* h, size_t bytes, void** ptr) {
+  if (!h || !ptr) return fail(A1MPC_EINVAL, "null argument");
+  CK(cudaSetDevice(h->device));
+  if (cudaMalloc(ptr, bytes) != cudaSuccess) { cudaGetLastError(); return fail(A1MPC_ENOMEM, "cudaMalloc failed"); }
+  return A1MPC_OK;
+}
+int a1mpc_device_free(a1mpc_handle* h, void* ptr) {
+  if (!h) return fail(A1MPC_EINVAL, "null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaFree(ptr));
+  return A1MPC_OK;
+}
+int a1mpc_host_alloc(a1mpc_handle* h, size_t bytes, void** ptr) {
+  if (!h || !ptr) return fail(A1MPC_EINVAL, "null argument");
+  CK(cudaSetDevice(h->device));
+  if (cudaMallocHost(ptr, bytes) != cudaSuccess) { cudaGetLastError(); return fail(A1MPC_ENOMEM, "cudaMallocHost failed"); }
+  return A1MPC_OK;
+}
+int a1mpc_host_free(a1mpc_handle* h, void* ptr) {
+  if (!h) return fail(A1MPC_EINVAL, "null argument");
+  CK(cudaFreeHost(ptr));
+  return A1MPC_OK;
+}
+int a1mpc_memcpy_h2d(a1mpc_handle* h, void* dst, const void* src, size_t bytes) {
+  if (!h) return fail(A1MPC_EINVAL, "null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  return A1MPC_OK;
+}
+int a1mpc_memcpy_d2h(a1mpc_handle* h, void* dst, const void* src, size_t bytes) {
+  if (!h) return fail(A1MPC_EINVAL, "null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  return A1MPC_OK;
+}
+int a1mpc_sync(a1mpc_handle* h) {
+  if (!h) return fail(A1MPC_EINVAL, "null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  return A1MPC_OK;
+}
+int a1mpc_event_create(a1mpc_handle* h, void** ev) {
+  if (!h || !ev) return fail(A1MPC_EINVAL, "null argument");
+  CK(cudaSetDevice(h->device));
+  cudaEvent_t e;
+  CK(cudaEventCreate(&e));
+  *ev = (void*)e;
+  return A1MPC_OK;
+}
+int a1mpc_event_destroy(a1mpc_handle* h, void* ev) {
+  if (!h) return fail(A1MPC_EINVAL, "null argument");
+  CK(cudaEventDestroy((cudaEvent_t)ev));
+  return A1MPC_OK;
+}
+int a1mpc_event_record(a1mpc_handle* h, void* ev) {
+  if (!h || !ev) return fail(A1MPC_EINVAL, "null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventRecord((cudaEvent_t)ev, h->stream));
+  return A1MPC_OK;
+}
+int a1mpc_event_elapsed_ms(a1mpc_handle* h, void* start, void* stop, float* ms) {
+  if (!h || !start || !stop || !ms) return fail(A1MPC_EINVAL, "null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventSynchronize((cudaEvent_t)stop));
+  CK(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  return A1MPC_OK;
+}
+int64_t a1mpc_launch_count(const a1mpc_handle* h) { return h ? h->launches : 0; }
+
+int a1mpc_measure_fp64_peak(a1mpc_handle* h, double* tflops) {
+  if (!h || !tflops) return fail(A1MPC_EINVAL, "null argument");
+  CK(cudaSetDevice(h->device));
+  const int threads = 256, blocks = h->sm_count * 8, iters = 1 << 16;
+  int rc;
+  if ((rc = ensure_side(h, (size_t)threads * blocks * 8))) return rc;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CK(cudaEventRecord(e0, h->stream));
+    fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>((double*)h->d_side, iters);
+    h->launches++;
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * (double)iters * threads * blocks;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) * 1e-12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops = best;
+  return A1MPC_OK;
+}
+
+int a1mpc_flush_l2(a1mpc_handle* h) {
+  if (!h) return fail(A1MPC_EINVAL, "null argument");
+  CK(cudaSetDevice(h->device));
+  if (!h->d_flush) {
+    h->flush_elems = (size_t)256 * 1024 * 1024 / 8;  // 256 MiB > 126 MB L2
+    if (cudaMalloc(&h->d_flush, h->flush_elems * 8) != cudaSuccess) { cudaGetLastError(); return fail(A1MPC_ENOMEM, "cudaMalloc failed"); }
+  }
+  flush_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(h->d_flush, h->flush_elems, 1.0);
+  h->launches++;
+  CK(cudaGetLastError());
+  return A1MPC_OK;
+}
+
+}  // extern "C"
+
+// accessors for a1mpc_nccl.cpp (which must not see the handle layout)
+extern "C" {
+void* a1mpc_internal_stream(a1mpc_handle* h) { return (void*)h->stream; }
+int a1mpc_internal_device(a1mpc_handle* h) { return h->device; }
+void** a1mpc_internal_nccl_slot(a1mpc_handle* h) { return &h->nccl_comm; }
+void a1mpc_internal_set_error(const char* msg) { g_err = msg; }
+}
