@@ -21,7 +21,7 @@ EXPORTS = [
     "a1mpc_grf_qp_batch", "a1mpc_device_alloc", "a1mpc_device_free", "a1mpc_host_alloc", "a1mpc_host_free",
     "a1mpc_memcpy_h2d", "a1mpc_memcpy_d2h", "a1mpc_sync", "a1mpc_event_create", "a1mpc_event_destroy",
     "a1mpc_event_record", "a1mpc_event_elapsed_ms", "a1mpc_launch_count", "a1mpc_measure_fp64_peak",
-    "a1mpc_flush_l2", "a1mpc_nccl_unique_id", "a1mpc_nccl_init", "a1mpc_allgather_forces", "a1mpc_gen_states",
+    "a1mpc_flush_l2", "a1mpc_profile_begin", "a1mpc_profile_end", "a1mpc_nccl_unique_id", "a1mpc_nccl_init", "a1mpc_allgather_forces", "a1mpc_gen_states",
 ]
 
 
@@ -75,6 +75,8 @@ def lib():
         l.a1mpc_grf_qp_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
         l.a1mpc_gen_states.argtypes = [C.c_int, C.c_uint64, C.c_int] + [C.c_void_p] * 5
         l.a1mpc_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        l.a1mpc_profile_begin.argtypes = [C.c_void_p, C.c_int]
+        l.a1mpc_profile_end.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         l.a1mpc_nccl_unique_id.argtypes = [C.c_void_p]
         l.a1mpc_nccl_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         l.a1mpc_allgather_forces.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -269,5 +271,26 @@ class Engine:
         _check(lib().a1mpc_measure_fp64_peak(self.h, C.byref(v)))
         return float(v.value)
 
+    def profile_begin(self, max_calls):
+        _check(lib().a1mpc_profile_begin(self.h, max_calls))
+
+    def profile_end(self):
+        ms = np.zeros(4); n = C.c_int()
+        _check(lib().a1mpc_profile_end(self.h, _p(ms), C.byref(n)))
+        return ms, int(n.value)
+
+    def nccl_init(self, nranks, rank, uid_bytes):
+        buf = C.create_string_buffer(bytes(uid_bytes), 128)
+        _check(lib().a1mpc_nccl_init(self.h, nranks, rank, buf))
+
+    def allgather_forces(self, f_local_ptr, f_all_ptr, B_local):
+        _check(lib().a1mpc_allgather_forces(self.h, f_local_ptr, f_all_ptr, B_local))
+
     def flush_l2(self):
         _check(lib().a1mpc_flush_l2(self.h))
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    _check(lib().a1mpc_nccl_unique_id(buf))
+    return bytes(buf.raw)

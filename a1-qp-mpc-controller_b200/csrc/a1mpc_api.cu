@@ -54,6 +54,10 @@ struct a1mpc_handle {
   double* d_flush = nullptr;
   size_t flush_elems = 0;
   int64_t launches = 0;
+  // optional per-class kernel timing (bench roofline): event pairs on the class streams
+  bool prof_on = false;
+  int prof_cap = 0, prof_n = 0;
+  std::vector<cudaEvent_t> prof_ev;  // [call][class 1..4][begin,end]
   // NCCL (dlopen'ed)
   void* nccl_lib = nullptr;
   void* nccl_comm = nullptr;
@@ -139,13 +143,17 @@ int enqueue_solve(a1mpc_handle* h, int B, const DevInputs& din, const DevOutputs
     cudaStream_t st = h->side[ns - 1];
     CK(cudaStreamWaitEvent(st, h->ev_fork, 0));
     const double* rec = h->d_rec + (size_t)(ns - 1) * h->cap * REC_DOUBLES;
+    const bool prof = h->prof_on && h->prof_n < h->prof_cap;
+    if (prof) CK(cudaEventRecord(h->prof_ev[((size_t)h->prof_n * 4 + (ns - 1)) * 2 + 0], st));
     if (!h->cls[ns].supported) unsupported_kernel<<<(B + 127) / 128, 128, 0, st>>>(rec, h->d_count, ns, dout, N);
     else if (N == 10) fused_launch_n10(ns, h->cls[ns], st, B, h->P, rec, h->d_count, dout);
     else fused_launch_n20(ns, h->cls[ns], st, B, h->P, rec, h->d_count, dout);
     h->launches++;
+    if (prof) CK(cudaEventRecord(h->prof_ev[((size_t)h->prof_n * 4 + (ns - 1)) * 2 + 1], st));
     CK(cudaEventRecord(h->ev_join[ns - 1], st));
     CK(cudaStreamWaitEvent(h->stream, h->ev_join[ns - 1], 0));
   }
+  if (h->prof_on && h->prof_n < h->prof_cap) h->prof_n++;
   CK(cudaGetLastError());
   return A1MPC_OK;
 }
@@ -251,6 +259,7 @@ int a1mpc_destroy(a1mpc_handle* h) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
   }
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -544,6 +553,37 @@ int a1mpc_measure_fp64_peak(a1mpc_handle* h, double* tflops) {
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   *tflops = best;
+  return A1MPC_OK;
+}
+
+int a1mpc_profile_begin(a1mpc_handle* h, int max_calls) {
+  if (!h || max_calls <= 0) return fail(A1MPC_EINVAL, "bad argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  while ((int)h->prof_ev.size() < max_calls * 8) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    h->prof_ev.push_back(e);
+  }
+  h->prof_cap = max_calls;
+  h->prof_n = 0;
+  h->prof_on = true;
+  return A1MPC_OK;
+}
+
+int a1mpc_profile_end(a1mpc_handle* h, double* ms_per_class4, int* calls) {
+  if (!h || !ms_per_class4) return fail(A1MPC_EINVAL, "null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < 4; ++k) ms_per_class4[k] = 0.0;
+  for (int c = 0; c < h->prof_n; ++c)
+    for (int k = 0; k < 4; ++k) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, h->prof_ev[((size_t)c * 4 + k) * 2], h->prof_ev[((size_t)c * 4 + k) * 2 + 1]));
+      ms_per_class4[k] += ms;
+    }
+  if (calls) *calls = h->prof_n;
+  h->prof_on = false;
   return A1MPC_OK;
 }
 

@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- convex-MPC QPs/s of the B200 engine (and, with --impl reference, of the CPU restatement
+of the reference path).  One JSON line on stdout (rank 0).
+
+A "step" is one a1mpc_solve_batch over one batch of synthetic trot-gait states:
+pack -> build (linearise + condense) -> QP solve -> force extraction, for B QPs per GPU.
+Default workload = BASELINE.json configs[1]: trot gait, horizon N=10, batch 1024, fp64, per GPU.
+Weak scaling: every rank solves its own B QPs (independent slices, no data-path collective); for N>1 the
+12 foot forces of every rank are all-gathered over NCCL after each step (config 5's final collect).
+
+Timing: CUDA events on the handle's stream around exactly K steps after W warm-up steps, barrier + device
+synchronise on both sides, max over ranks.  Inputs rotate through a ring of distinct batches larger than L2.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "a1-qp-mpc-controller_b200"))
+sys.path.insert(0, ROOT)
+
+METRIC = "convex-MPC QPs/sec (N=10, batched)"
+UNIT = "QPs/s"
+L2_BYTES = 126e6
+IN_BYTES_PER_QP = 42 * 8 + 4     # x0[12] rot[9] foot[12] ref[9] fp64 + contact mask
+OUT_BYTES_PER_QP = 12 * 8 + 4    # f_body[12] fp64 + status
+ALG_BYTES_PER_QP = IN_BYTES_PER_QP + OUT_BYTES_PER_QP   # 440 B
+
+
+def algorithmic_flops(N, ns_hist, iters_by_class):
+    """build counted as the reference formulates it + solve = factorizations*(n^3/3 + 4 n^2 + 30 n)"""
+    build = 2 * 13 ** 3 * (N - 1) + 2 * 13 * 13 * 12 * N * (N - 1) / 2 + 2 * (12 * N) ** 2 * 13 * N + 2 * 13 * N * 13 + 2 * 12 * N * 13 * N
+    total_alg = 0.0
+    total_exec = 0.0
+    for ns, cnt in ns_hist.items():
+        if ns == 0 or cnt == 0:
+            continue
+        n = 3 * ns * N
+        per_fact = n ** 3 / 3.0 + 4.0 * n * n + 30.0 * n
+        it = iters_by_class.get(ns, 0.0)
+        total_alg += cnt * (build + it * per_fact)
+        # what this engine executes instead of the dense build: two Gram blocks + closed-form gradient
+        A = 3 * ns
+        build_exec = 2 * 2 * 6 * A * A + 2 * 12 * n + 40 * N * N
+        total_exec += cnt * (build_exec + it * per_fact)
+    return total_alg, total_exec
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons while the GPU is under load (B200_PROFILING.md recipe)"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            p = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    """torch.distributed is plumbing only: barrier + MAX over ranks of the device-timed milliseconds"""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+            dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        else:
+            dist_mod.init_process_group(backend="gloo")
+        dist = dist_mod
+    return rank, world, local, dist
+
+
+def dist_barrier(dist):
+    if dist is not None:
+        dist.barrier()
+
+
+def dist_max(dist, value):
+    if dist is None:
+        return value
+    import torch
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if torch.cuda.is_available() else torch.device("cpu")
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def dist_bcast_bytes(dist, payload, rank):
+    if dist is None:
+        return payload
+    obj = [payload if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    return obj[0]
+
+
+def cpu_reference_rate(cfg_kw, st, nthreads, target_seconds, O):
+    """reference path restated on CPU (dense build + OSQP-algorithm at default settings, cold start)"""
+    ocfg = O.make_config(**cfg_kw)
+    B = st["x0"].shape[1]
+    probe = min(B, 8 * nthreads)
+    ob = O.Batch(st["x0"][:, :probe], st["rot"][:, :probe], st["foot"][:, :probe], st["ref"][:, :probe], st["contact"][:probe])
+    sec, _ = O.time_reference_path(ocfg, ob, nthreads)
+    rate = probe / max(sec, 1e-9)
+    S = int(min(B, max(probe, rate * target_seconds)))
+    ob = O.Batch(st["x0"][:, :S], st["rot"][:, :S], st["foot"][:, :S], st["ref"][:, :S], st["contact"][:S])
+    sec, _ = O.time_reference_path(ocfg, ob, nthreads)
+    return S / sec, S, sec
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm (restated: Eigen/OSQP/ROS are not installable
+    offline, so oracle/_ref does not exist) on all host threads, same metric/config."""
+    from oracle import oracle_py as O
+    rank, world, local, dist = dist_setup(args.gpus)
+    if rank != 0:
+        return
+    import a1mpc
+    nthreads = O.hardware_threads()
+    B = args.batch
+    st = a1mpc.gen_states(B, 2, 0)
+    cfg_kw = dict(horizon=args.horizon)
+    ocfg = O.make_config(**cfg_kw)
+    # bounded sample per step so that warmup+steps end within a few minutes
+    probe = min(B, 4 * nthreads)
+    ob = O.Batch(st["x0"][:, :probe], st["rot"][:, :probe], st["foot"][:, :probe], st["ref"][:, :probe], st["contact"][:probe])
+    sec, _ = O.time_reference_path(ocfg, ob, nthreads)
+    rate = probe / max(sec, 1e-9)
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    S = int(min(B, max(nthreads, rate * min(budget, 3.0))))
+    ob = O.Batch(st["x0"][:, :S], st["rot"][:, :S], st["foot"][:, :S], st["ref"][:, :S], st["contact"][:S])
+    for _ in range(args.warmup):
+        O.time_reference_path(ocfg, ob, nthreads)
+    t = 0.0
+    for _ in range(args.steps):
+        sec, _ = O.time_reference_path(ocfg, ob, nthreads)
+        t += sec
+    value = S * args.steps / t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "trot gait convex MPC, horizon N=%d, batch %d per GPU, fp64 (BASELINE configs[1])" % (args.horizon, B),
+                       "sample_qps_per_step": S},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port",
+                             "sample": "%d QPs of the workload batch per step, dense ConvexMpc build + OSQP-algorithm restatement at OSQP defaults, cold start, one QP per task" % S},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--batch", type=int, default=1024, help="QPs per GPU per step (configs[1]: 1024; config 5 shard: 32768)")
+    ap.add_argument("--horizon", type=int, default=10)
+    ap.add_argument("--config-id", type=int, default=2, help="2: trot narrow noise, 4: wide noise")
+    ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import a1mpc
+    rank, world, local, dist = dist_setup(args.gpus)
+    n_gpus = world if world > 1 else 1
+    B, N, K, W = args.batch, args.horizon, args.steps, args.warmup
+    cfg = a1mpc.default_config(horizon=N)
+    eng = a1mpc.Engine(cfg, device=local)
+
+    # ---- ring of distinct input batches, total bytes > L2 so that no step finds its inputs cached ----
+    ring = int(np.ceil(1.05 * L2_BYTES / (IN_BYTES_PER_QP * B)))
+    ring = max(2, min(ring, max(K, 2)))
+    dev, host = [], []
+    for r in range(ring):
+        st = a1mpc.gen_states(B, args.config_id, stream=rank * 1000003 + r)
+        d = a1mpc.DeviceBatch(eng, B, want_u=False, want_iters=(r == 0))
+        d.upload(st)
+        dev.append(d)
+        if r < 8:
+            host.append(st)
+    ring_bytes = ring * IN_BYTES_PER_QP * B
+
+    # ---- optional final collect of the forces over NCCL (config 5) ----
+    gather = None
+    gather_err = None
+    if n_gpus > 1 and not args.no_gather:
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("nvidia.nccl")
+            if spec and spec.submodule_search_locations:
+                cand = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    os.environ.setdefault("A1MPC_NCCL_LIB", cand)
+            uid = a1mpc.nccl_unique_id() if rank == 0 else None
+            uid = dist_bcast_bytes(dist, uid, rank)
+            eng.nccl_init(n_gpus, rank, uid)
+            gather = eng.dalloc(n_gpus * 12 * B * 8)
+        except Exception as e:  # reported, never silent
+            gather = None
+            gather_err = str(e)
+
+    def step(i):
+        d = dev[i % ring]
+        eng.solve_ptrs(B, d.inp, d.out)
+        if gather is not None:
+            eng.allgather_forces(d.f_body, gather, B)
+
+    # ---- warm-up ----
+    for i in range(W):
+        step(i)
+    eng.sync()
+    f0, status0 = dev[0].download()
+    iters0 = np.zeros(B, dtype=np.int32)
+    a1mpc._check(a1mpc.lib().a1mpc_memcpy_d2h(eng.h, iters0.ctypes.data, dev[0].iters, iters0.nbytes))
+    eng.sync()
+
+    # ---- timed region: exactly K steps ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    e0, e1 = eng.event(), eng.event()
+    launches0 = eng.launches()
+    eng.profile_begin(K)
+    dist_barrier(dist)
+    eng.sync()
+    t_wall0 = time.time()
+    eng.record(e0)
+    for i in range(K):
+        step(W + i)
+    eng.record(e1)
+    eng.sync()
+    dist_barrier(dist)
+    t_wall1 = time.time()
+    ms_local = eng.elapsed_ms(e0, e1)
+    class_ms, ncalls = eng.profile_end()
+    launches = eng.launches() - launches0
+    ms = dist_max(dist, ms_local)
+    value = n_gpus * B * K / (ms * 1e-3)
+
+    # ---- per-step latency distribution (p50 solve us), separate pass with a sync per step ----
+    lat = []
+    ea, eb = eng.event(), eng.event()
+    for i in range(min(K, 300)):
+        eng.record(ea)
+        step(i)
+        eng.record(eb)
+        lat.append(eng.elapsed_ms(ea, eb) * 1e3)
+    lat = np.array(lat)
+
+    # ---- end to end through the public host-pointer call: pinned host inputs, H2D + solve + D2H each step ----
+    hp = []
+    for st in host:
+        p = {k: eng.pinned_array(st[k].shape, st[k].dtype) for k in st}
+        for k in st:
+            p[k][...] = st[k]
+        hp.append(p)
+    f_pin = eng.pinned_array((12, B), np.float64)
+    s_pin = eng.pinned_array((B,), np.int32)
+    Ke = min(K, 400)
+
+    def e2e_step(i):
+        p = hp[i % len(hp)]
+        inp = a1mpc.Inputs(p["x0"].ctypes.data, p["rot"].ctypes.data, p["foot"].ctypes.data, p["ref"].ctypes.data, p["contact"].ctypes.data, B)
+        out = a1mpc.Outputs(f_pin.ctypes.data, s_pin.ctypes.data, None, None, B)
+        eng.solve_ptrs(B, inp, out)
+
+    for i in range(3):
+        e2e_step(i)
+    dist_barrier(dist)
+    eng.sync()
+    tw0 = time.time()
+    eng.record(e0)
+    for i in range(Ke):
+        e2e_step(i)
+    eng.record(e1)
+    eng.sync()
+    dist_barrier(dist)
+    e2e_ms = dist_max(dist, eng.elapsed_ms(e0, e1))
+    e2e_wall = time.time() - tw0
+    e2e_value = n_gpus * B * Ke / (max(e2e_ms, 1e3 * 0) * 1e-3)
+    clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (most device time among the class kernels) ----
+    ns_of = np.array([bin(int(c) & 15).count("1") for c in host[0]["contact"]])
+    hist = {ns: int((ns_of == ns).sum()) for ns in range(5)}
+    dom = int(np.argmax(class_ms)) + 1
+    dom_ms = class_ms[dom - 1] / max(ncalls, 1)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    dom_qps = hist.get(dom, 0)
+    achieved_gbs = ALG_BYTES_PER_QP * dom_qps / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    it_by_class = {}
+    for ns in range(1, 5):
+        m = ns_of == ns
+        if m.any():
+            it_by_class[ns] = float(np.mean(iters0[m] % 100 + iters0[m] // 100))   # factorizations per QP
+    fl_alg, fl_exec = algorithmic_flops(N, {dom: dom_qps}, it_by_class)
+    fp64_peak = eng.fp64_peak_tflops()
+    roofline = {"bound": "hbm", "kernel": "solve_kernel<NS=%d,N=%d>" % (dom, N), "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_qp": ALG_BYTES_PER_QP, "qps_per_launch": dom_qps, "kernel_ms": dom_ms,
+                "note": "the path is fp64-pipe/latency bound (SURVEY 8d: ~1e4 FLOP/B), so the HBM fraction is small by construction; see roofline_fp64"}
+    roofline_fp64 = {"bound": "fp64-fma-pipe", "kernel": roofline["kernel"], "unit": "TFLOP/s",
+                     "achieved_algorithmic": fl_alg / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0,
+                     "achieved_executed": fl_exec / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0,
+                     "peak": fp64_peak, "peak_source": "measured in this run (a1mpc_measure_fp64_peak: dependent-free DFMA stream)",
+                     "frac": (fl_exec / (dom_ms * 1e-3) / 1e12) / fp64_peak if dom_ms > 0 and fp64_peak > 0 else None,
+                     "factorizations_per_qp": it_by_class}
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle_py as O
+        nthreads = O.hardware_threads()
+        v, S, sec = cpu_reference_rate(dict(horizon=N), host[0], nthreads, args.cpu_seconds, O)
+        v1, S1, sec1 = cpu_reference_rate(dict(horizon=N), host[0], 1, 2.0, O)
+        cpu = {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port",
+               "sample": "%d QPs of the step batch in %.1f s; dense ConvexMpc build + OSQP-algorithm restatement at OSQP defaults (eps 1e-3), cold start" % (S, sec),
+               "single_thread_value": v1}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "trot gait convex MPC, horizon N=%d, batch %d per GPU, fp64 (BASELINE configs[1]%s)" % (N, B, "" if (B == 1024 and N == 10) else " variant"),
+                       "horizon": N, "batch_per_gpu": B, "global_batch": B * n_gpus, "generator": "a1mpc_gen_states config_id=%d" % args.config_id,
+                       "cache": "inputs rotate through a ring of %d distinct batches = %.0f MB > L2 (126 MB)" % (ring, ring_bytes / 1e6),
+                       "stance_feet_histogram": hist,
+                       "final_collect": ("ncclAllGather of [12][B] forces per step" if gather is not None else ("none" if n_gpus == 1 or args.no_gather else "unavailable: %s" % gather_err))},
+            "p50_solve_us": float(np.percentile(lat, 50)), "p99_solve_us": float(np.percentile(lat, 99)),
+            "p50_solve_us_per_qp": float(np.percentile(lat, 50)) / B,
+            "status_histogram": {int(k): int(v) for k, v in zip(*np.unique(status0, return_counts=True))},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": IN_BYTES_PER_QP * B, "d2h_bytes_per_step": OUT_BYTES_PER_QP * B,
+                    "steps": Ke, "wall_s": e2e_wall},
+            "gpu_launches": launches,
+            "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu, "clocks": clocks,
+            "class_kernel_ms_per_step": {int(i + 1): float(class_ms[i] / max(ncalls, 1)) for i in range(4)}}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

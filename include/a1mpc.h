@@ -167,6 +167,11 @@ int  a1mpc_event_elapsed_ms(a1mpc_handle* h, void* start, void* stop, float* ms)
 int64_t a1mpc_launch_count(const a1mpc_handle* h);
 /* measured peak of the fp64 FMA pipe on this device, TFLOP/s (dependent-free DFMA stream) */
 int  a1mpc_measure_fp64_peak(a1mpc_handle* h, double* tflops);
+/* Per-class kernel timing for roofline reports: between begin and end every a1mpc_solve_batch records a
+ * CUDA-event pair around each class kernel ON THE STREAM THAT KERNEL RUNS ON (up to max_calls calls).
+ * end() synchronises and returns the summed device time in ms of the kernels for 1,2,3,4 stance feet. */
+int  a1mpc_profile_begin(a1mpc_handle* h, int max_calls);
+int  a1mpc_profile_end(a1mpc_handle* h, double* ms_per_class4, int* calls);
 /* writes one buffer larger than L2 (flushes L2 between timed iterations when asked to) */
 int  a1mpc_flush_l2(a1mpc_handle* h);
 

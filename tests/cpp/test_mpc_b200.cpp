@@ -1,0 +1,76 @@
+// test_mpc_b200.cpp -- the reference's only standalone driver of the hot path (src/a1_cpp/src/test/test_mpc.cpp)
+// re-expressed on the batched shims: same hand-built state, same call sequence
+//   ConvexMpc(q,r) -> reset -> calculate_A_mat_c -> N x {calculate_B_mat_c, state_space_discretization, store}
+//   -> calculate_qp_mats -> solver.solve() -> getSolution()
+// plus the compute_grf entry point on the same state.  Unlike the reference it checks the result
+// (exit code != 0 on mismatch with the KKT-certified optimum of this fixture).
+#include <cmath>
+#include <cstdio>
+
+#include "A1MpcBatch.h"
+
+using namespace a1mpc_host;
+
+int main() {
+  const int N = 10;
+  A1CtrlStatesLite state;
+  const double robot_mass = 15;
+  const double a1_trunk_inertia[9] = {0.0158533, 0, 0, 0, 0.0377999, 0, 0, 0, 0.0456542};
+  state.root_pos[2] = 0.15;
+  const double foot_pos_rel[12] = {0.17, 0.17, -0.17, -0.17, 0.15, -0.15, 0.15, -0.15, -0.35, -0.35, -0.35, -0.35};
+  for (int k = 0; k < 12; ++k) state.foot_pos_abs[k] = foot_pos_rel[k];
+  state.contacts[0] = true; state.contacts[1] = false; state.contacts[2] = true; state.contacts[3] = false;
+  const double dt = 0.0025;
+  const double q_weights[13] = {1.0, 1.0, 1.0, 0.0, 0.0, 50.0, 0.0, 0.0, 1.0, 1.0, 1.0, 1.0, 0.0};
+  double r_weights[12];
+  for (int i = 0; i < 12; ++i) r_weights[i] = 1e-6;
+
+  // ---- ConvexMpc path (test_mpc.cpp:61-151) ----
+  ConvexMpcBatch mpc_solver(1, q_weights, r_weights, N, 0);
+  mpc_solver.reset();
+  double mpc_states[13] = {0, 0, 0, 0, 0, 0.15, 0, 0, 0, 0, 0, 0, -9.8};
+  double mpc_states_d[13 * N];
+  for (int i = 0; i < N; ++i) {
+    double* d = &mpc_states_d[13 * i];
+    for (int k = 0; k < 13; ++k) d[k] = 0;
+    d[5] = 0.15;
+    d[12] = -9.8;
+  }
+  mpc_solver.calculate_A_mat_c(0, state.root_euler);
+  for (int i = 0; i < N; ++i) {
+    mpc_solver.calculate_B_mat_c(0, robot_mass, a1_trunk_inertia, state.root_rot_mat, state.foot_pos_abs);
+    mpc_solver.state_space_discretization(0, dt);
+    mpc_solver.store_B_mat_d(0, i);
+  }
+  mpc_solver.set_states(0, mpc_states, mpc_states_d, state.contacts);
+  mpc_solver.calculate_qp_mats();
+  mpc_solver.solve();
+  std::printf("ConvexMpcBatch + solve():\n");
+  for (int a = 0; a < 3; ++a) {
+    for (int i = 0; i < 4; ++i) std::printf("%14.8f ", mpc_solver.solution[3 * i + a]);
+    std::printf("\n");
+  }
+  // ---- compute_grf path ----
+  A1RobotControlBatch ctrl(robot_mass, a1_trunk_inertia, q_weights, r_weights, N, 0);
+  state.root_pos_d[2] = 0.15;
+  std::vector<A1CtrlStatesLite> states(3, state);   // a batch of three identical robots
+  std::vector<std::array<double, 12>> grf;
+  std::vector<int32_t> status;
+  ctrl.compute_grf(states, dt, grf, &status);
+  std::printf("A1RobotControlBatch::compute_grf (robot 2 of 3):\n");
+  for (int a = 0; a < 3; ++a) {
+    for (int i = 0; i < 4; ++i) std::printf("%14.8f ", grf[2][a * 4 + i]);
+    std::printf("\n");
+  }
+  const double want[3] = {0.0, -12.8370306335, 42.7901021118};
+  double err = 0;
+  for (int a = 0; a < 3; ++a) {
+    for (int leg : {0, 2}) {
+      err = std::fmax(err, std::fabs(mpc_solver.solution[3 * leg + a] - want[a]));
+      err = std::fmax(err, std::fabs(grf[2][a * 4 + leg] - want[a]));
+    }
+    for (int leg : {1, 3}) err = std::fmax(err, std::fabs(mpc_solver.solution[3 * leg + a]) + std::fabs(grf[0][a * 4 + leg]));
+  }
+  std::printf("max |f - f*| = %.3e N, status %d %d\n", err, (int)mpc_solver.status[0], (int)status[2]);
+  return (err <= 1e-4 && mpc_solver.status[0] == 0 && status[2] == 0) ? 0 : 1;
+}

@@ -1,0 +1,40 @@
+"""world_size-2 gloo test of bench.py's multi-rank plumbing (barrier, MAX over ranks, id broadcast, per-rank
+shards of the synthetic workload).  CPU only; the GPU path uses the same helpers with the nccl backend."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, json
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "a1-qp-mpc-controller_b200"))
+import numpy as np
+import bench, a1mpc
+rank, world, local, dist = bench.dist_setup(2)
+assert world == 2 and dist is not None
+bench.dist_barrier(dist)
+m = bench.dist_max(dist, 10.0 + rank)          # max over ranks of the per-rank device time
+assert m == 11.0, m
+uid = bench.dist_bcast_bytes(dist, b"x" * 128 if rank == 0 else None, rank)
+assert uid == b"x" * 128
+st = a1mpc.gen_states(256, 2, stream=rank * 1000003)     # each rank owns an independent slice
+import torch
+t = torch.tensor(st["x0"][:, :4].copy())
+out = [torch.zeros_like(t) for _ in range(2)]
+dist.all_gather(out, t)
+assert not torch.equal(out[0], out[1])                   # shards differ
+assert torch.equal(out[rank], t)
+bench.dist_barrier(dist)
+print("RANK_OK", rank)
+'''
+
+
+def test_two_rank_plumbing(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(WORKER % (ROOT, ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29617", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29617", str(script)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "RANK_OK 0" in r.stdout and "RANK_OK 1" in r.stdout
