@@ -192,10 +192,10 @@ __global__ void __launch_bounds__(32) dense_solve_kernel(const __grid_constant__
       }
       for (int v = lane; v < NV; v += 32) c.g[v] = gb[full(v)] * gsc;
       __syncwarp();
-      fill_padding<NS, N>(c);
+      fill_padding<NS, N, 0>(c);
       DenseHess<NS, N> hp;
       hp.Hs = Hs;
-      st = solve_qp<NS, N>(c, hp, P, iters);
+      st = solve_qp<NS, N, 0, DenseHess<NS, N>, DirectLS<NS, N, DenseHess<NS, N>>>(c, hp, P, iters);
     }
     for (int e = lane; e < n; e += 32) {
       const int s = e / 12, r = e - 12 * s, leg = r / 3, a = r - 3 * leg;
@@ -302,10 +302,10 @@ __global__ void __launch_bounds__(32) grf_qp_kernel(const __grid_constant__ DevP
       }
       if (lane < NV) c.g[lane] = gv * gsc;
       __syncwarp();
-      fill_padding<NS, 1>(c);
+      fill_padding<NS, 1, 0>(c);
       DenseHess<NS, 1> hp;
       hp.Hs = Hs;
-      st = solve_qp<NS, 1>(c, hp, P, iters);
+      st = solve_qp<NS, 1, 0, DenseHess<NS, 1>, DirectLS<NS, 1, DenseHess<NS, 1>>>(c, hp, P, iters);
     }
     // :439-444  foot_forces_grf = root_rot_mat^T * QPSolution
     if (lane < 4) {

@@ -3,15 +3,15 @@
 
 namespace a1mpc {
 
-template <int NS, int N, int WPC>
+template <int NS, int N, int WPC, int LSM>
 static cudaError_t setup_one(int sm_count, ClassLaunch& c) {
-  using G = Geo<NS, N>;
+  using G = Geo<NS, N, LSM>;
   c.wpc = WPC;
   c.smem = G::smem_bytes(WPC);
-  cudaError_t e = cudaFuncSetAttribute(solve_kernel<NS, N, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+  cudaError_t e = cudaFuncSetAttribute(solve_kernel<NS, N, WPC, LSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<NS, N, WPC>, 32 * WPC, c.smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<NS, N, WPC, LSM>, 32 * WPC, c.smem);
   if (e != cudaSuccess) return e;
   if (occ < 1) return cudaErrorLaunchOutOfResources;
   c.max_ctas = occ * sm_count;
@@ -19,12 +19,12 @@ static cudaError_t setup_one(int sm_count, ClassLaunch& c) {
   return cudaSuccess;
 }
 
-template <int NS, int N, int WPC>
+template <int NS, int N, int WPC, int LSM>
 static void launch_one(const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count, const DevOutputs& out) {
   int grid = (B + WPC - 1) / WPC;
   if (grid > c.max_ctas) grid = c.max_ctas;
   if (grid < 1) grid = 1;
-  solve_kernel<NS, N, WPC><<<grid, 32 * WPC, c.smem, st>>>(P, rec, count, out);
+  solve_kernel<NS, N, WPC, LSM><<<grid, 32 * WPC, c.smem, st>>>(P, rec, count, out);
 }
 
 #ifndef A1MPC_HORIZON
@@ -34,32 +34,32 @@ static void launch_one(const ClassLaunch& c, cudaStream_t st, int B, const DevPa
 #if A1MPC_HORIZON == 10
 cudaError_t fused_setup_n10(int sm_count, ClassLaunch (&cls)[5]) {
   cudaError_t e;
-  if ((e = setup_one<1, 10, 4>(sm_count, cls[1])) != cudaSuccess) return e;
-  if ((e = setup_one<2, 10, 2>(sm_count, cls[2])) != cudaSuccess) return e;
-  if ((e = setup_one<3, 10, 1>(sm_count, cls[3])) != cudaSuccess) return e;
-  if ((e = setup_one<4, 10, 1>(sm_count, cls[4])) != cudaSuccess) return e;
+  if ((e = setup_one<1, 10, 4, 0>(sm_count, cls[1])) != cudaSuccess) return e;
+  if ((e = setup_one<2, 10, 2, 0>(sm_count, cls[2])) != cudaSuccess) return e;
+  if ((e = setup_one<3, 10, 2, 1>(sm_count, cls[3])) != cudaSuccess) return e;
+  if ((e = setup_one<4, 10, 2, 1>(sm_count, cls[4])) != cudaSuccess) return e;
   return cudaSuccess;
 }
 void fused_launch_n10(int ns, const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count, const DevOutputs& out) {
-  if (ns == 1) launch_one<1, 10, 4>(c, st, B, P, rec, count, out);
-  if (ns == 2) launch_one<2, 10, 2>(c, st, B, P, rec, count, out);
-  if (ns == 3) launch_one<3, 10, 1>(c, st, B, P, rec, count, out);
-  if (ns == 4) launch_one<4, 10, 1>(c, st, B, P, rec, count, out);
+  if (ns == 1) launch_one<1, 10, 4, 0>(c, st, B, P, rec, count, out);
+  if (ns == 2) launch_one<2, 10, 2, 0>(c, st, B, P, rec, count, out);
+  if (ns == 3) launch_one<3, 10, 2, 1>(c, st, B, P, rec, count, out);
+  if (ns == 4) launch_one<4, 10, 2, 1>(c, st, B, P, rec, count, out);
 }
 #else
 cudaError_t fused_setup_n20(int sm_count, ClassLaunch (&cls)[5]) {
   cudaError_t e;
-  if ((e = setup_one<1, 20, 2>(sm_count, cls[1])) != cudaSuccess) return e;
-  if ((e = setup_one<2, 20, 1>(sm_count, cls[2])) != cudaSuccess) return e;
-  if ((e = setup_one<3, 20, 1>(sm_count, cls[3])) != cudaSuccess) return e;
-  cls[4].supported = false;  // 240 x 240 fp64 factor exceeds 227 KB of shared memory
+  if ((e = setup_one<1, 20, 2, 0>(sm_count, cls[1])) != cudaSuccess) return e;
+  if ((e = setup_one<2, 20, 1, 0>(sm_count, cls[2])) != cudaSuccess) return e;
+  if ((e = setup_one<3, 20, 1, 1>(sm_count, cls[3])) != cudaSuccess) return e;
+  if ((e = setup_one<4, 20, 1, 1>(sm_count, cls[4])) != cudaSuccess) return e;
   return cudaSuccess;
 }
 void fused_launch_n20(int ns, const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count, const DevOutputs& out) {
-  if (ns == 1) launch_one<1, 20, 2>(c, st, B, P, rec, count, out);
-  if (ns == 2) launch_one<2, 20, 1>(c, st, B, P, rec, count, out);
-  if (ns == 3) launch_one<3, 20, 1>(c, st, B, P, rec, count, out);
-  // ns == 4: the 240 x 240 fp64 factor does not fit; a1mpc_api.cu marks those QPs (unsupported_kernel)
+  if (ns == 1) launch_one<1, 20, 2, 0>(c, st, B, P, rec, count, out);
+  if (ns == 2) launch_one<2, 20, 1, 0>(c, st, B, P, rec, count, out);
+  if (ns == 3) launch_one<3, 20, 1, 1>(c, st, B, P, rec, count, out);
+  if (ns == 4) launch_one<4, 20, 1, 1>(c, st, B, P, rec, count, out);
 }
 #endif
 

@@ -125,7 +125,7 @@ def solve_wrench(st, par, N=10, fscale=100.0, mu_switch=1e-9, dense_check=None):
 
             def solve(rc):
                 rhs = -rd + C.T @ (rc / s - w * rp)
-                dx = WK.solve(rhs); ds_ = -rp - C @ dx; dl = -(rc + lam * ds_) / s
+                dx = WK.solve0(rhs); ds_ = -rp - C @ dx; dl = -(rc + lam * ds_) / s
                 return dx, ds_, dl
             dxa, dsa, dla = solve(s * lam)
             aa = min(amax(s, dsa), amax(lam, dla)); mu_aff = (s + aa * dsa) @ (lam + aa * dla) / m
