@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liba1mpc.so")
+LIB_PATH = os.environ.get("A1MPC_LIB", os.path.join(_HERE, "liba1mpc.so"))   # A1MPC_LIB: developer A/B builds only
 
 STATUS_OPTIMAL, STATUS_IPM_ONLY, STATUS_MAXITER, STATUS_NUMERICAL, STATUS_NO_CONTACT = 0, 1, 2, 3, 4
 

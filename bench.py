@@ -137,17 +137,17 @@ def dist_bcast_bytes(dist, payload, rank):
     return obj[0]
 
 
-def cpu_reference_rate(cfg_kw, st, nthreads, target_seconds, O):
-    """reference path restated on CPU (dense build + OSQP-algorithm at default settings, cold start)"""
+def cpu_reference_rate(cfg_kw, config_id, nthreads, target_seconds, O, a1mpc):
+    """reference path restated on CPU (dense build + OSQP-algorithm at default settings, cold start) on a bounded
+    sample of the same synthetic workload (same generator, same distribution), sized for ~target_seconds"""
     ocfg = O.make_config(**cfg_kw)
-    B = st["x0"].shape[1]
-    probe = min(B, 8 * nthreads)
-    ob = O.Batch(st["x0"][:, :probe], st["rot"][:, :probe], st["foot"][:, :probe], st["ref"][:, :probe], st["contact"][:probe])
-    sec, _ = O.time_reference_path(ocfg, ob, nthreads)
+    probe = 16 * nthreads
+    st = a1mpc.gen_states(probe, config_id, stream=777)
+    sec, _ = O.time_reference_path(ocfg, O.Batch(st["x0"], st["rot"], st["foot"], st["ref"], st["contact"]), nthreads)
     rate = probe / max(sec, 1e-9)
-    S = int(min(B, max(probe, rate * target_seconds)))
-    ob = O.Batch(st["x0"][:, :S], st["rot"][:, :S], st["foot"][:, :S], st["ref"][:, :S], st["contact"][:S])
-    sec, _ = O.time_reference_path(ocfg, ob, nthreads)
+    S = int(max(probe, min(rate * target_seconds, 4e6)))
+    st = a1mpc.gen_states(S, config_id, stream=778)
+    sec, _ = O.time_reference_path(ocfg, O.Batch(st["x0"], st["rot"], st["foot"], st["ref"], st["contact"]), nthreads)
     return S / sec, S, sec
 
 
@@ -161,17 +161,17 @@ def run_reference(args):
     import a1mpc
     nthreads = O.hardware_threads()
     B = args.batch
-    st = a1mpc.gen_states(B, 2, 0)
     cfg_kw = dict(horizon=args.horizon)
     ocfg = O.make_config(**cfg_kw)
     # bounded sample per step so that warmup+steps end within a few minutes
-    probe = min(B, 4 * nthreads)
-    ob = O.Batch(st["x0"][:, :probe], st["rot"][:, :probe], st["foot"][:, :probe], st["ref"][:, :probe], st["contact"][:probe])
-    sec, _ = O.time_reference_path(ocfg, ob, nthreads)
+    probe = 16 * nthreads
+    stp = a1mpc.gen_states(probe, 2, 777)
+    sec, _ = O.time_reference_path(ocfg, O.Batch(stp["x0"], stp["rot"], stp["foot"], stp["ref"], stp["contact"]), nthreads)
     rate = probe / max(sec, 1e-9)
-    budget = 120.0 / max(1, args.steps + args.warmup)
-    S = int(min(B, max(nthreads, rate * min(budget, 3.0))))
-    ob = O.Batch(st["x0"][:, :S], st["rot"][:, :S], st["foot"][:, :S], st["ref"][:, :S], st["contact"][:S])
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    S = int(max(16 * nthreads, rate * min(budget, 4.0)))
+    st = a1mpc.gen_states(S, 2, 778)
+    ob = O.Batch(st["x0"], st["rot"], st["foot"], st["ref"], st["contact"])
     for _ in range(args.warmup):
         O.time_reference_path(ocfg, ob, nthreads)
     t = 0.0
@@ -185,7 +185,7 @@ def run_reference(args):
             "config": {"workload": "trot gait convex MPC, horizon N=%d, batch %d per GPU, fp64 (BASELINE configs[1])" % (args.horizon, B),
                        "sample_qps_per_step": S},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port",
-                             "sample": "%d QPs of the workload batch per step, dense ConvexMpc build + OSQP-algorithm restatement at OSQP defaults, cold start, one QP per task" % S},
+                             "sample": "%d synthetic QPs (same generator/distribution as the workload) per step, dense ConvexMpc build + OSQP-algorithm restatement at OSQP defaults, cold start, one QP per task" % S},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -353,8 +353,17 @@ def main():
             it_by_class[ns] = float(np.mean(iters0[m] % 100 + iters0[m] // 100))   # factorizations per QP
     fl_alg, fl_exec = algorithmic_flops(N, {dom: dom_qps}, it_by_class)
     fp64_peak = eng.fp64_peak_tflops()
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tj.get("solve_kernel<NS=%d,N=%d>@%d" % (dom, N, B))
+        if ent:
+            traffic = ent["dram_bytes_read"] + ent["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "solve_kernel<NS=%d,N=%d>" % (dom, N), "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved_gbs / hbm_peak, "traffic": traffic, "traffic_source": "ncu dram__bytes_read+write of one launch, profiles/traffic.json" if traffic else None,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_qp": ALG_BYTES_PER_QP, "qps_per_launch": dom_qps, "kernel_ms": dom_ms,
                 "note": "the path is fp64-pipe/latency bound (SURVEY 8d: ~1e4 FLOP/B), so the HBM fraction is small by construction; see roofline_fp64"}
     roofline_fp64 = {"bound": "fp64-fma-pipe", "kernel": roofline["kernel"], "unit": "TFLOP/s",
@@ -367,10 +376,10 @@ def main():
     if not args.no_cpu_baseline:
         from oracle import oracle_py as O
         nthreads = O.hardware_threads()
-        v, S, sec = cpu_reference_rate(dict(horizon=N), host[0], nthreads, args.cpu_seconds, O)
-        v1, S1, sec1 = cpu_reference_rate(dict(horizon=N), host[0], 1, 2.0, O)
+        v, S, sec = cpu_reference_rate(dict(horizon=N), args.config_id, nthreads, args.cpu_seconds, O, a1mpc)
+        v1, S1, sec1 = cpu_reference_rate(dict(horizon=N), args.config_id, 1, 2.0, O, a1mpc)
         cpu = {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port",
-               "sample": "%d QPs of the step batch in %.1f s; dense ConvexMpc build + OSQP-algorithm restatement at OSQP defaults (eps 1e-3), cold start" % (S, sec),
+               "sample": "%d synthetic QPs (same generator/distribution as the step batch) in %.1f s; dense ConvexMpc build + OSQP-algorithm restatement at OSQP defaults (eps 1e-3), cold start" % (S, sec),
                "single_thread_value": v1}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
