@@ -401,3 +401,9 @@ def main():
 
 if __name__ == "__main__":
     main()
+    try:
+        import torch.distributed as _d
+        if _d.is_available() and _d.is_initialized():
+            _d.destroy_process_group()
+    except Exception:
+        pass
