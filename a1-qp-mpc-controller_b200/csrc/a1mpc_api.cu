@@ -459,6 +459,40 @@ int a1mpc_grf_qp_batch(a1mpc_handle* h, int B, const double* root_acc, const dou
   return A1MPC_OK;
 }
 
+int a1mpc_joint_torques_batch(a1mpc_handle* h, int B, const double* f_grf, const double* f_kin, const double* jac, const uint32_t* contact,
+                              const double* km_foot, const double* torques_gravity, double* tau) {
+  if (!h || !f_grf || !f_kin || !jac || !contact || !km_foot || !torques_gravity || !tau) return fail(A1MPC_EINVAL, "null argument");
+  if (B <= 0) return fail(A1MPC_EINVAL, "B must be positive");
+  CK(cudaSetDevice(h->device));
+  const bool dev = is_device_ptr(f_grf);
+  const size_t Bs = (size_t)B;
+  TorqueParams P;
+  for (int i = 0; i < 3; ++i) P.km[i] = km_foot[i];
+  for (int i = 0; i < 12; ++i) P.tg[i] = torques_gravity[i];
+  const double *dg = f_grf, *dk = f_kin, *dj = jac;
+  const uint32_t* dc = contact;
+  double* dt = tau;
+  int rc;
+  if (!dev) {
+    if ((rc = ensure_side(h, Bs * (12 + 12 + 36 + 12) * 8 + Bs * 4))) return rc;
+    double* p = (double*)h->d_side;
+    CK(cudaMemcpyAsync(p, f_grf, Bs * 12 * 8, cudaMemcpyHostToDevice, h->stream)); dg = p; p += Bs * 12;
+    CK(cudaMemcpyAsync(p, f_kin, Bs * 12 * 8, cudaMemcpyHostToDevice, h->stream)); dk = p; p += Bs * 12;
+    CK(cudaMemcpyAsync(p, jac, Bs * 36 * 8, cudaMemcpyHostToDevice, h->stream)); dj = p; p += Bs * 36;
+    CK(cudaMemcpyAsync(p, tau, Bs * 12 * 8, cudaMemcpyHostToDevice, h->stream)); dt = p; p += Bs * 12;
+    uint32_t* pc = (uint32_t*)p;
+    CK(cudaMemcpyAsync(pc, contact, Bs * 4, cudaMemcpyHostToDevice, h->stream)); dc = pc;
+  }
+  joint_torques_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(B, dg, dk, dj, dc, P, dt);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (!dev) {
+    CK(cudaMemcpyAsync(tau, dt, Bs * 12 * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return A1MPC_OK;
+}
+
 // ---- helpers -------------------------------------------------------------------------------
 int a1mpc_device_alloc(a1mpc_handle* h, size_t bytes, void** ptr) {
   if (!h || !ptr) return fail(A1MPC_EINVAL, "null argument");

@@ -49,6 +49,60 @@ __global__ void unsupported_kernel(const double* __restrict__ rec, const int* __
     for (int k = 0; k < 12 * horizon; ++k) out.u_full[(size_t)k * out.ld + b] = 0.0;
 }
 
+// compute_joint_torques (A1RobotControl.cpp:289-319): thread per QP, every access batch-major coalesced.  HBM bound:
+// (12+12+36+12) fp64 + 4 B read, 12 fp64 written per QP = 676 B/QP.
+struct TorqueParams { double km[3]; double tg[12]; };
+__global__ void joint_torques_kernel(int B, const double* __restrict__ f_grf, const double* __restrict__ f_kin,
+                                     const double* __restrict__ jac, const uint32_t* __restrict__ contact, TorqueParams P,
+                                     double* __restrict__ tau) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const size_t ld = (size_t)B;
+  const uint32_t mask = contact[b];
+#pragma unroll
+  for (int leg = 0; leg < 4; ++leg) {
+    double J[9], t[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) J[k] = jac[(size_t)(9 * leg + k) * ld + b];
+    if ((mask >> leg) & 1u) {   // stance: J^T * (-f)
+      const double f0 = -f_grf[(size_t)(3 * leg) * ld + b], f1 = -f_grf[(size_t)(3 * leg + 1) * ld + b], f2 = -f_grf[(size_t)(3 * leg + 2) * ld + b];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) t[a] = J[a] * f0 + J[3 + a] * f1 + J[6 + a] * f2;
+    } else {                    // swing: solve J tau = km .* f_kin with partial pivoting (Eigen's jac.lu().solve)
+      double r[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) r[a] = P.km[a] * f_kin[(size_t)(3 * leg + a) * ld + b];
+      // column 0 pivot
+      int p = 0;
+      if (fabs(J[3]) > fabs(J[p * 3])) p = 1;
+      if (fabs(J[6]) > fabs(J[p * 3])) p = 2;
+      if (p != 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const double x = J[k]; J[k] = J[3 * p + k]; J[3 * p + k] = x; }
+        const double x = r[0]; r[0] = r[p]; r[p] = x;
+      }
+      double m1 = J[3] / J[0], m2 = J[6] / J[0];
+      J[4] -= m1 * J[1]; J[5] -= m1 * J[2]; r[1] -= m1 * r[0];
+      J[7] -= m2 * J[1]; J[8] -= m2 * J[2]; r[2] -= m2 * r[0];
+      if (fabs(J[7]) > fabs(J[4])) {
+        double x = J[4]; J[4] = J[7]; J[7] = x;
+        x = J[5]; J[5] = J[8]; J[8] = x;
+        x = r[1]; r[1] = r[2]; r[2] = x;
+      }
+      const double m3 = J[7] / J[4];
+      J[8] -= m3 * J[5]; r[2] -= m3 * r[1];
+      t[2] = r[2] / J[8];
+      t[1] = (r[1] - J[5] * t[2]) / J[4];
+      t[0] = (r[0] - J[1] * t[1] - J[2] * t[2]) / J[0];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double v = t[a] + P.tg[3 * leg + a];
+      if (v == v) tau[(size_t)(3 * leg + a) * ld + b] = v;   // "prevent nan" (:314-317)
+    }
+  }
+}
+
 // fp64 FMA pipe peak probe: 8 independent dependent-free DFMA chains per thread
 __global__ void fp64_peak_kernel(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;

@@ -151,6 +151,18 @@ int  a1mpc_grf_qp_batch(a1mpc_handle* h, int B, const double* root_acc, const do
                         const double* rot, const double* foot, const uint32_t* contact,
                         double* f_body, int32_t* status);
 
+/* ---- the step right after the path: A1RobotControl::compute_joint_torques ------------- */
+/* A1RobotControl.cpp:289-319, batched, batch-major SoA like a1mpc_solve_batch (ld = B), host or device pointers:
+ *   f_grf   [12][B]  foot_forces_grf, leg-major (the f_body output of a1mpc_solve_batch can be passed as is)
+ *   f_kin   [12][B]  foot_forces_kin, leg-major (swing-leg PD force, A1RobotControl.cpp:286)
+ *   jac     [36][B]  the four 3x3 diagonal blocks of j_foot, leg-major then row-major (A1CtrlStates.h:409)
+ *   contact [B]      bit i = contacts[i]
+ *   km_foot[3], torques_gravity[12]: batch-uniform (A1CtrlStates.h:122,129)
+ *   tau     [12][B]  in/out: stance legs  J^T (-f_grf),  swing legs  J^-1 (km_foot .* f_kin)  (partial-pivot LU),
+ *                    + torques_gravity; an entry whose result is NaN keeps its previous value (:314-317). */
+int  a1mpc_joint_torques_batch(a1mpc_handle* h, int B, const double* f_grf, const double* f_kin, const double* jac,
+                               const uint32_t* contact, const double* km_foot, const double* torques_gravity, double* tau);
+
 /* ---- device memory, stream and timing helpers (so hosts need no CUDA headers) -------------- */
 int  a1mpc_device_alloc(a1mpc_handle* h, size_t bytes, void** ptr);
 int  a1mpc_device_free(a1mpc_handle* h, void* ptr);

@@ -1138,6 +1138,47 @@ int oracle_grf_qp_single(const double* root_acc, const double* rot_z, const doub
   return 0;
 }
 
+// A1RobotControl::compute_joint_torques (A1RobotControl.cpp:289-319) for one robot.  jac: four 3x3 row-major blocks,
+// f_grf / f_kin leg-major, tau in/out (NaN results keep the previous value).  Partial-pivot LU like Eigen's lu().
+int oracle_joint_torques(const double* f_grf, const double* f_kin, const double* jac, uint32_t contact, const double* km_foot,
+                         const double* torques_gravity, double* tau) {
+  for (int leg = 0; leg < 4; ++leg) {
+    const double* J = jac + 9 * leg;
+    double t[3];
+    if ((contact >> leg) & 1u) {
+      for (int a = 0; a < 3; ++a) t[a] = J[a] * -f_grf[3 * leg] + J[3 + a] * -f_grf[3 * leg + 1] + J[6 + a] * -f_grf[3 * leg + 2];
+    } else {
+      long double A[3][4];
+      for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) A[i][j] = J[3 * i + j];
+        A[i][3] = (long double)km_foot[i] * f_kin[3 * leg + i];
+      }
+      for (int c = 0; c < 3; ++c) {
+        int p = c;
+        for (int i = c + 1; i < 3; ++i)
+          if (fabsl(A[i][c]) > fabsl(A[p][c])) p = i;
+        for (int j = 0; j < 4; ++j) std::swap(A[c][j], A[p][j]);
+        for (int i = c + 1; i < 3; ++i) {
+          long double m = A[i][c] / A[c][c];
+          for (int j = c; j < 4; ++j) A[i][j] -= m * A[c][j];
+        }
+      }
+      long double x[3];
+      for (int i = 2; i >= 0; --i) {
+        long double s = A[i][3];
+        for (int j = i + 1; j < 3; ++j) s -= A[i][j] * x[j];
+        x[i] = s / A[i][i];
+      }
+      for (int a = 0; a < 3; ++a) t[a] = (double)x[a];
+    }
+    for (int a = 0; a < 3; ++a) {
+      double v = t[a] + torques_gravity[3 * leg + a];
+      if (!std::isnan(v)) tau[3 * leg + a] = v;
+    }
+  }
+  return 0;
+}
+
 // wall-clock timing of the reference-faithful path (build + OSQP default, cold start) on nthreads
 double oracle_time_reference_path(const a1mpc_config* cfg, int B, const a1mpc_inputs* in, int nthreads, double* f_body) {
   auto t0 = std::chrono::steady_clock::now();

@@ -129,6 +129,14 @@ def grf_qp_single(root_acc, rot_z, rot, foot, contact, mode=MODE_EXACT):
     return f, info
 
 
+def joint_torques(f_grf, f_kin, jac, contact, km_foot, torques_gravity, tau_prev=None):
+    """one robot: f_grf[12], f_kin[12], jac[36] -> tau[12]"""
+    tau = np.zeros(12) if tau_prev is None else np.array(tau_prev, dtype=np.float64)
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (f_grf, f_kin, jac, km_foot, torques_gravity)]
+    lib().oracle_joint_torques(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), C.c_uint32(int(contact)), _ptr(a[3]), _ptr(a[4]), _ptr(tau))
+    return tau
+
+
 def time_reference_path(cfg, batch, nthreads):
     f = np.zeros((12, batch.B))
     inp = batch.c_inputs()

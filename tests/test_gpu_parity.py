@@ -245,6 +245,25 @@ def test_grf_qp_branch(a1, O, gpu_engine):
         assert np.abs(f[b] - fo).max() <= TOL_F, (b, np.abs(f[b] - fo).max())
 
 
+def test_joint_torques_next_row(a1, O, gpu_engine):
+    """SURVEY 8f.1: A1RobotControl::compute_joint_torques (A1RobotControl.cpp:289-319), fed straight from the solver's forces"""
+    B = 512
+    st = a1.gen_states(B, 2, 121)
+    f, status, _ = gpu_engine.solve(st)
+    rng = np.random.default_rng(9)
+    jac = (0.2 * np.eye(3).reshape(1, 3, 3, 1) + 0.15 * rng.standard_normal((4, 3, 3, B))).reshape(36, B)
+    f_kin = 30.0 * rng.standard_normal((12, B))
+    km = np.array([0.1, 0.1, 0.1]); tg = np.array([0.8, 0, 0, -0.8, 0, 0, 0.8, 0, 0, -0.8, 0, 0])
+    prev = rng.standard_normal((12, B))
+    f_kin[4, 7] = np.nan                      # a NaN result keeps the previous torque (A1RobotControl.cpp:314-317)
+    st["contact"][7] = 0b1101
+    tau = gpu_engine.joint_torques(f, f_kin, jac, st["contact"], km, tg, tau_prev=prev)
+    for b in range(0, B, 7):
+        to = O.joint_torques(f[:, b], f_kin[:, b], jac[:, b], st["contact"][b], km, tg, tau_prev=prev[:, b])
+        assert np.allclose(tau[:, b], to, rtol=1e-10, atol=1e-10, equal_nan=True), b
+    assert np.array_equal(tau[3:6, 7], prev[3:6, 7])      # swing leg 1 of robot 7: NaN force -> all three torques NaN -> kept
+
+
 def test_fp64_peak_probe_and_profile_api(a1, gpu_engine):
     assert 20.0 < gpu_engine.fp64_peak_tflops() < 80.0     # B200 fp64 FMA pipe ~ 37-40 TFLOP/s
     st = a1.gen_states(512, 2, 111)
