@@ -231,8 +231,12 @@ int a1mpc_create(a1mpc_handle** out, const a1mpc_config* cfg, int device) {
   int rc = A1MPC_OK;
   auto bail = [&](int code) { a1mpc_destroy(h); return code; };
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(A1MPC_ECUDA, "stream create failed"));
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   for (int i = 0; i < 4; ++i) {
-    if (cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking) != cudaSuccess) return bail(fail(A1MPC_ECUDA, "stream create failed"));
+    // the classes with more stance feet take longer per QP: their CTAs are placed first
+    const int prio = (i >= 2) ? prio_hi : prio_lo;
+    if (cudaStreamCreateWithPriority(&h->side[i], cudaStreamNonBlocking, prio) != cudaSuccess) return bail(fail(A1MPC_ECUDA, "stream create failed"));
     if (cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) != cudaSuccess) return bail(fail(A1MPC_ECUDA, "event create failed"));
   }
   if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(fail(A1MPC_ECUDA, "event create failed"));
