@@ -33,8 +33,11 @@ OUT_BYTES_PER_QP = 12 * 8 + 4    # f_body[12] fp64 + status
 ALG_BYTES_PER_QP = IN_BYTES_PER_QP + OUT_BYTES_PER_QP   # 440 B
 
 
-def algorithmic_flops(N, ns_hist, iters_by_class):
-    """build counted as the reference formulates it + solve = factorizations*(n^3/3 + 4 n^2 + 30 n)"""
+def algorithmic_flops(N, ns_hist, fact_by_class):
+    """FLOPs per launch of one class kernel.
+    algorithmic: build counted as the reference formulates it + factorizations * (n^3/3 + 4 n^2 + 30 n), n = 3*NS*N
+    executed: what this engine does instead -- closed-form build (two Gram blocks + gradient), and per factorization either the
+              n x n Cholesky + two solve pairs (NS <= 2) or the 6N x 6N wrench-space core + block products (NS >= 3)"""
     build = 2 * 13 ** 3 * (N - 1) + 2 * 13 * 13 * 12 * N * (N - 1) / 2 + 2 * (12 * N) ** 2 * 13 * N + 2 * 13 * N * 13 + 2 * 12 * N * 13 * N
     total_alg = 0.0
     total_exec = 0.0
@@ -42,12 +45,16 @@ def algorithmic_flops(N, ns_hist, iters_by_class):
         if ns == 0 or cnt == 0:
             continue
         n = 3 * ns * N
-        per_fact = n ** 3 / 3.0 + 4.0 * n * n + 30.0 * n
-        it = iters_by_class.get(ns, 0.0)
-        total_alg += cnt * (build + it * per_fact)
-        # what this engine executes instead of the dense build: two Gram blocks + closed-form gradient
+        it = fact_by_class.get(ns, 0.0)
+        total_alg += cnt * (build + it * (n ** 3 / 3.0 + 4.0 * n * n + 30.0 * n))
         A = 3 * ns
         build_exec = 2 * 2 * 6 * A * A + 2 * 12 * n + 40 * N * N
+        if ns <= 2:
+            per_fact = n ** 3 / 3.0 + 4.0 * n * n + 2 * (2 * N + 2 * A) * n + 30.0 * n
+        else:
+            nc = 6 * N
+            kr = (N * (N + 1) / 2) * (2 * 6 * 6 * 6 + 2 * 36 * 3)
+            per_fact = nc ** 3 / 3.0 + kr + 4.0 * nc * nc + 4 * (2 * N + 12) * 2 * nc + 2 * (18 + 18 + 18) * ns * N * 2 + 60.0 * n
         total_exec += cnt * (build_exec + it * per_fact)
     return total_alg, total_exec
 

@@ -86,7 +86,7 @@ struct ConvexMpcRestated {
   double mu, fz_min, fz_max;
   std::vector<double> q_weights_mpc, r_weights_mpc;  // tiled, un-doubled (ConvexMpc.cpp:16-19, 37-40)
   Mat linear_constraints;                            // 20N x 12N (ConvexMpc.cpp:46-58)
-  Mat A_mat_c, B_mat_c, A_mat_d, B_mat_d, B_mat_d_list, A_qp, B_qp, hessian;
+  Mat A_mat_c, B_mat_c, A_mat_d, B_mat_d, B_mat_d_list, A_qp, B_qp, hessian, QB_;
   std::vector<double> gradient, lb, ub;
 
   ConvexMpcRestated(int N_, const double* q, const double* r, double mu_, double fzmin, double fzmax)
@@ -111,10 +111,26 @@ struct ConvexMpcRestated {
     }
     reset();
   }
-  void reset() {  // ConvexMpc.cpp:70-108
-    A_mat_c = Mat(13, 13); B_mat_c = Mat(13, 12); A_mat_d = Mat(13, 13); B_mat_d = Mat(13, 12);
-    B_mat_d_list = Mat(13 * N, 12); A_qp = Mat(13 * N, 13); B_qp = Mat(13 * N, 12 * N);
-    hessian = Mat(12 * N, 12 * N);
+  void reinit(const double* q, const double* r) {  // the per-tick part of the constructor (ConvexMpc.cpp:16-58)
+    for (int i = 0; i < N; ++i) {
+      for (int k = 0; k < 13; ++k) q_weights_mpc[13 * i + k] = q[k];
+      for (int k = 0; k < 12; ++k) r_weights_mpc[12 * i + k] = r[k];
+    }
+    for (int i = 0; i < 4 * N; ++i) {
+      linear_constraints(0 + 5 * i, 0 + 3 * i) = 1; linear_constraints(1 + 5 * i, 0 + 3 * i) = 1;
+      linear_constraints(2 + 5 * i, 1 + 3 * i) = 1; linear_constraints(3 + 5 * i, 1 + 3 * i) = 1;
+      linear_constraints(4 + 5 * i, 2 + 3 * i) = 1;
+      linear_constraints(0 + 5 * i, 2 + 3 * i) = mu; linear_constraints(1 + 5 * i, 2 + 3 * i) = -mu;
+      linear_constraints(2 + 5 * i, 2 + 3 * i) = mu; linear_constraints(3 + 5 * i, 2 + 3 * i) = -mu;
+    }
+  }
+  void reset() {  // ConvexMpc.cpp:70-108 (setZero on fixed-size members: no reallocation)
+    auto z = [](Mat& m, int r, int c) {
+      if (m.r != r || m.c != c) m = Mat(r, c);
+      else std::fill(m.a.begin(), m.a.end(), 0.0);
+    };
+    z(A_mat_c, 13, 13); z(B_mat_c, 13, 12); z(A_mat_d, 13, 13); z(B_mat_d, 13, 12);
+    z(B_mat_d_list, 13 * N, 12); z(A_qp, 13 * N, 13); z(B_qp, 13 * N, 12 * N); z(hessian, 12 * N, 12 * N);
     gradient.assign(12 * N, 0.0); lb.assign(20 * N, 0.0); ub.assign(20 * N, 0.0);
   }
   void calculate_A_mat_c(const double* root_euler) {  // ConvexMpc.cpp:110-130
@@ -185,7 +201,8 @@ struct ConvexMpcRestated {
     }
     // hessian :207-211   dense_hessian = B_qp^T * Q * B_qp ; += R   with Q = 2 q, R = 2 r
     const int n = nu * N, ns = nx * N;
-    Mat QB(ns, n);
+    if (QB_.r != ns || QB_.c != n) QB_ = Mat(ns, n);
+    Mat& QB = QB_;
     for (int i = 0; i < ns; ++i) {
       double w = 2 * q_weights_mpc[i];
       for (int j = 0; j < n; ++j) QB(i, j) = w * B_qp(i, j);
@@ -969,13 +986,19 @@ int oracle_qp_mats(const a1mpc_config* cfg, const double* A_d, const double* B_d
 }
 
 // info[8]: iters, status/verified, kkt_stat, kkt_prim, kkt_dual, rounds, pri_res, dua_res
+// The reference constructs a ConvexMpc per control tick (A1RobotControl.cpp:447) out of fixed-size Eigen members, i.e.
+// without heap traffic; the restatement keeps one object per worker thread so that the multi-threaded baseline is not
+// throttled by mmap/munmap of its 100 KB matrices (the constructor's work -- tiling weights, filling the pyramid -- is
+// repeated per QP through reinit()).
 static int solve_one(const a1mpc_config* cfg, const a1mpc_inputs* in, int b, int mode, double eps, double* f_body,
-                     double* u_full, double* info8) {
+                     double* u_full, double* info8, ConvexMpcRestated* ws = nullptr) {
   const int N = cfg->horizon;
   const int n = 12 * N, m = 20 * N;
   RobotState st;
   unpack(in, b, &st);
-  ConvexMpcRestated mpc(N, cfg->q, cfg->r, cfg->mu, cfg->fz_min, cfg->fz_max);
+  ConvexMpcRestated local_or_ws = ws ? ConvexMpcRestated(1, cfg->q, cfg->r, cfg->mu, cfg->fz_min, cfg->fz_max) : ConvexMpcRestated(N, cfg->q, cfg->r, cfg->mu, cfg->fz_min, cfg->fz_max);
+  ConvexMpcRestated& mpc = ws ? *ws : local_or_ws;
+  if (ws) ws->reinit(cfg->q, cfg->r);
   std::vector<double> x0, xd, sol(n, 0.0);
   drive_convex_mpc(mpc, *cfg, st, x0, xd);
   if (info8) std::fill(info8, info8 + 8, 0.0);
@@ -1013,11 +1036,12 @@ int oracle_compute_grf_batch(const a1mpc_config* cfg, int B, const a1mpc_inputs*
   const int n = 12 * cfg->horizon;
   std::atomic<int> next(0);
   auto work = [&]() {
+    ConvexMpcRestated ws(cfg->horizon, cfg->q, cfg->r, cfg->mu, cfg->fz_min, cfg->fz_max);
     for (;;) {
       int b = next.fetch_add(1);
       if (b >= B) break;
       double f[12];
-      solve_one(cfg, in, b, mode, eps, f, u_full ? u_full + (size_t)b * n : nullptr, info ? info + (size_t)b * 8 : nullptr);
+      solve_one(cfg, in, b, mode, eps, f, u_full ? u_full + (size_t)b * n : nullptr, info ? info + (size_t)b * 8 : nullptr, &ws);
       if (f_body)
         for (int k = 0; k < 12; ++k) f_body[(size_t)k * B + b] = f[k];
     }
