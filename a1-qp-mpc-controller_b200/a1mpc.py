@@ -17,11 +17,11 @@ STATUS_OPTIMAL, STATUS_IPM_ONLY, STATUS_MAXITER, STATUS_NUMERICAL, STATUS_NO_CON
 
 EXPORTS = [
     "a1mpc_default_config", "a1mpc_create", "a1mpc_destroy", "a1mpc_last_error", "a1mpc_device_count",
-    "a1mpc_solve_batch", "a1mpc_build_qp_batch", "a1mpc_qp_mats_batch", "a1mpc_solve_dense_batch",
+    "a1mpc_solve_batch", "a1mpc_solve_batch_ext", "a1mpc_build_qp_batch", "a1mpc_qp_mats_batch", "a1mpc_solve_dense_batch",
     "a1mpc_grf_qp_batch", "a1mpc_joint_torques_batch", "a1mpc_device_alloc", "a1mpc_device_free", "a1mpc_host_alloc", "a1mpc_host_free",
     "a1mpc_memcpy_h2d", "a1mpc_memcpy_d2h", "a1mpc_sync", "a1mpc_event_create", "a1mpc_event_destroy",
     "a1mpc_event_record", "a1mpc_event_elapsed_ms", "a1mpc_launch_count", "a1mpc_measure_fp64_peak",
-    "a1mpc_flush_l2", "a1mpc_profile_begin", "a1mpc_profile_end", "a1mpc_nccl_unique_id", "a1mpc_nccl_init", "a1mpc_allgather_forces", "a1mpc_gen_states",
+    "a1mpc_flush_l2", "a1mpc_profile_begin", "a1mpc_profile_end", "a1mpc_nccl_unique_id", "a1mpc_nccl_init", "a1mpc_allgather_forces", "a1mpc_gen_states", "a1mpc_gen_schedule",
 ]
 
 
@@ -36,6 +36,10 @@ class Config(C.Structure):
 class Inputs(C.Structure):
     _fields_ = [("x0", C.c_void_p), ("rot", C.c_void_p), ("foot", C.c_void_p), ("ref", C.c_void_p),
                 ("contact", C.c_void_p), ("ld", C.c_size_t)]
+
+
+class InputsExt(C.Structure):
+    _fields_ = [("contact_sched", C.c_void_p), ("normals", C.c_void_p)]
 
 
 class Outputs(C.Structure):
@@ -69,6 +73,8 @@ def lib():
         l.a1mpc_event_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         l.a1mpc_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         l.a1mpc_solve_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Inputs), C.POINTER(Outputs)]
+        l.a1mpc_solve_batch_ext.argtypes = [C.c_void_p, C.c_int, C.POINTER(Inputs), C.POINTER(InputsExt), C.POINTER(Outputs)]
+        l.a1mpc_gen_schedule.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         l.a1mpc_build_qp_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Inputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         l.a1mpc_qp_mats_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
         l.a1mpc_solve_dense_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
@@ -116,6 +122,13 @@ def gen_states(B, config_id=2, stream=0):
     rc = lib().a1mpc_gen_states(config_id, stream, B, _p(x0), _p(rot), _p(foot), _p(ref), _p(contact))
     _check(rc)
     return dict(x0=x0, rot=rot, foot=foot, ref=ref, contact=contact)
+
+
+def gen_schedule(B, horizon, config_id=4, stream=0):
+    """config-4 extras: per-step contact schedule [N,B] and per-foot terrain normals [12,B]"""
+    sched = np.zeros((horizon, B), dtype=np.uint32); normals = np.zeros((12, B))
+    _check(lib().a1mpc_gen_schedule(config_id, stream, B, horizon, _p(sched), _p(normals)))
+    return sched, normals
 
 
 class DeviceBatch:
@@ -187,6 +200,21 @@ class Engine:
         inp = Inputs(_p(a["x0"]), _p(a["rot"]), _p(a["foot"]), _p(a["ref"]), _p(a["contact"]), B)
         out = Outputs(_p(f), _p(status), _p(iters), _p(u), B)
         _check(lib().a1mpc_solve_batch(self.h, B, C.byref(inp), C.byref(out)))
+        return (f, status, iters, u) if want_u else (f, status, iters)
+
+    def solve_ext(self, st, sched=None, normals=None, want_u=False):
+        """BASELINE config 4 (extension): per-step contact schedule [N,B] and/or terrain normals [12,B]"""
+        B = st["x0"].shape[1]
+        N = self.cfg.horizon
+        a = {k: np.ascontiguousarray(st[k], dtype=(np.uint32 if k == "contact" else np.float64)) for k in ("x0", "rot", "foot", "ref", "contact")}
+        sc = np.ascontiguousarray(sched, dtype=np.uint32) if sched is not None else None
+        nm = np.ascontiguousarray(normals, dtype=np.float64) if normals is not None else None
+        f = np.zeros((12, B)); status = np.zeros(B, dtype=np.int32); iters = np.zeros(B, dtype=np.int32)
+        u = np.zeros((12 * N, B)) if want_u else None
+        inp = Inputs(_p(a["x0"]), _p(a["rot"]), _p(a["foot"]), _p(a["ref"]), _p(a["contact"]), B)
+        ext = InputsExt(_p(sc), _p(nm))
+        out = Outputs(_p(f), _p(status), _p(iters), _p(u), B)
+        _check(lib().a1mpc_solve_batch_ext(self.h, B, C.byref(inp), C.byref(ext), C.byref(out)))
         return (f, status, iters, u) if want_u else (f, status, iters)
 
     def solve_ptrs(self, B, inp, out):

@@ -37,6 +37,12 @@ struct a1mpc_handle {
   a1mpc_config cfg;
   DevParams P;
   a1mpc::ClassLaunch cls[5];  // index = number of stance feet
+  a1mpc::ClassLaunch cls_ext;  // extended path (config 4)
+  double* d_rec_ext = nullptr;
+  size_t cap_ext = 0;
+  uint32_t* d_sched = nullptr;
+  double* d_normals = nullptr;
+  size_t cap_ext_mirror = 0;
   // scratch sized for `cap` QPs
   size_t cap = 0;
   double* d_rec = nullptr;
@@ -244,6 +250,8 @@ int a1mpc_create(a1mpc_handle** out, const a1mpc_config* cfg, int device) {
   {
     cudaError_t e = (cfg->horizon == 10) ? fused_setup_n10(h->sm_count, h->cls) : fused_setup_n20(h->sm_count, h->cls);
     if (e != cudaSuccess) return bail(fail(A1MPC_ECUDA, std::string("kernel setup: ") + cudaGetErrorString(e)));
+    e = ext_setup(cfg->horizon, h->sm_count, h->cls_ext);
+    if (e != cudaSuccess) return bail(fail(A1MPC_ECUDA, std::string("ext kernel setup: ") + cudaGetErrorString(e)));
     e = dense_setup(cfg->horizon);
     if (e != cudaSuccess) return bail(fail(A1MPC_ECUDA, std::string("dense kernel setup: ") + cudaGetErrorString(e)));
   }
@@ -259,6 +267,7 @@ int a1mpc_destroy(a1mpc_handle* h) {
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(h->d_rec); fr(h->d_count); fr(h->d_x0); fr(h->d_rot); fr(h->d_foot); fr(h->d_ref); fr(h->d_f); fr(h->d_u);
   fr(h->d_contact); fr(h->d_status); fr(h->d_iters); fr(h->d_side); fr(h->d_flush); fr(h->d_lists);
+  fr(h->d_rec_ext); fr(h->d_sched); fr(h->d_normals);
   for (int i = 0; i < 4; ++i) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
@@ -302,6 +311,77 @@ int a1mpc_solve_batch(a1mpc_handle* h, int B, const a1mpc_inputs* in, const a1mp
   if (out->u_full)
     if ((rc = copy_rows(h->stream, out->u_full, out->ld, h->d_u, Bs, 12 * h->cfg.horizon, Bs, 8, cudaMemcpyDeviceToHost))) return rc;
   CK(cudaStreamSynchronize(h->stream));
+  return A1MPC_OK;
+}
+
+int a1mpc_solve_batch_ext(a1mpc_handle* h, int B, const a1mpc_inputs* in, const a1mpc_inputs_ext* ext, const a1mpc_outputs* out) {
+  if (!h || !in || !out) return fail(A1MPC_EINVAL, "null argument");
+  if (!ext || (!ext->contact_sched && !ext->normals)) return a1mpc_solve_batch(h, B, in, out);
+  if (B <= 0) return fail(A1MPC_EINVAL, "B must be positive");
+  if (!in->x0 || !in->rot || !in->foot || !in->ref || !in->contact || !out->f_body || !out->status) return fail(A1MPC_EINVAL, "null input/output array");
+  if (in->ld < (size_t)B || out->ld < (size_t)B) return fail(A1MPC_EINVAL, "ld < B");
+  if (ext->normals)
+    for (int i = 0; i < 4; ++i)
+      if (h->cfg.r[3 * i] != h->cfg.r[3 * i + 1] || h->cfg.r[3 * i] != h->cfg.r[3 * i + 2])
+        return fail(A1MPC_EINVAL, "terrain normals need isotropic r weights per foot (r[3i] == r[3i+1] == r[3i+2])");
+  CK(cudaSetDevice(h->device));
+  const int N = h->cfg.horizon;
+  const size_t Bs = (size_t)B;
+  const bool dev = is_device_ptr(in->x0);
+  if (dev != is_device_ptr(out->f_body) || (ext->contact_sched && dev != is_device_ptr(ext->contact_sched)) || (ext->normals && dev != is_device_ptr(ext->normals)))
+    return fail(A1MPC_EINVAL, "inputs and outputs must be all-host or all-device");
+  int rc;
+  if ((rc = ensure_capacity(h, B, !dev, !dev && out->u_full != nullptr))) return rc;
+  if (Bs > h->cap_ext) {
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->d_rec_ext) cudaFree(h->d_rec_ext);
+    h->d_rec_ext = nullptr;
+    CK(cudaMalloc(&h->d_rec_ext, h->cap * REC_EXT_BYTES));
+    h->cap_ext = h->cap;
+  }
+  DevInputs di{in->x0, in->rot, in->foot, in->ref, in->contact, in->ld};
+  DevOutputs dout{out->f_body, out->status, out->iters, out->u_full, out->ld};
+  const uint32_t* dsched = ext->contact_sched;
+  const double* dnorm = ext->normals;
+  if (!dev) {
+    if (Bs > h->cap_ext_mirror) {
+      CK(cudaStreamSynchronize(h->stream));
+      if (h->d_sched) cudaFree(h->d_sched);
+      if (h->d_normals) cudaFree(h->d_normals);
+      h->d_sched = nullptr; h->d_normals = nullptr;
+      CK(cudaMalloc(&h->d_sched, (size_t)A1MPC_MAX_HORIZON * h->cap * 4));
+      CK(cudaMalloc(&h->d_normals, 12 * h->cap * 8));
+      h->cap_ext_mirror = h->cap;
+    }
+    if ((rc = copy_rows(h->stream, h->d_x0, Bs, in->x0, in->ld, 12, Bs, 8, cudaMemcpyHostToDevice))) return rc;
+    if ((rc = copy_rows(h->stream, h->d_rot, Bs, in->rot, in->ld, 9, Bs, 8, cudaMemcpyHostToDevice))) return rc;
+    if ((rc = copy_rows(h->stream, h->d_foot, Bs, in->foot, in->ld, 12, Bs, 8, cudaMemcpyHostToDevice))) return rc;
+    if ((rc = copy_rows(h->stream, h->d_ref, Bs, in->ref, in->ld, 9, Bs, 8, cudaMemcpyHostToDevice))) return rc;
+    CK(cudaMemcpyAsync(h->d_contact, in->contact, Bs * 4, cudaMemcpyHostToDevice, h->stream));
+    if (ext->contact_sched) {
+      if ((rc = copy_rows(h->stream, h->d_sched, Bs, ext->contact_sched, in->ld, N, Bs, 4, cudaMemcpyHostToDevice))) return rc;
+      dsched = h->d_sched;
+    }
+    if (ext->normals) {
+      if ((rc = copy_rows(h->stream, h->d_normals, Bs, ext->normals, in->ld, 12, Bs, 8, cudaMemcpyHostToDevice))) return rc;
+      dnorm = h->d_normals;
+    }
+    di = DevInputs{h->d_x0, h->d_rot, h->d_foot, h->d_ref, h->d_contact, Bs};
+    dout = DevOutputs{h->d_f, h->d_status, out->iters ? h->d_iters : nullptr, out->u_full ? h->d_u : nullptr, Bs};
+  }
+  CK(cudaMemsetAsync(h->d_count, 0, 8 * sizeof(int), h->stream));
+  pack_ext_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(di, dsched, dnorm, B, h->d_rec_ext, h->d_count, dout, N);
+  ext_launch(N, h->cls_ext, h->stream, B, h->P, h->d_rec_ext, h->d_count, dout);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  if (!dev) {
+    if ((rc = copy_rows(h->stream, out->f_body, out->ld, h->d_f, Bs, 12, Bs, 8, cudaMemcpyDeviceToHost))) return rc;
+    CK(cudaMemcpyAsync(out->status, h->d_status, Bs * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (out->iters) CK(cudaMemcpyAsync(out->iters, h->d_iters, Bs * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (out->u_full)
+      if ((rc = copy_rows(h->stream, out->u_full, out->ld, h->d_u, Bs, 12 * N, Bs, 8, cudaMemcpyDeviceToHost))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+  }
   return A1MPC_OK;
 }
 

@@ -66,3 +66,36 @@ extern "C" int a1mpc_gen_states(int config_id, uint64_t stream, int B, double* x
   }
   return A1MPC_OK;
 }
+
+extern "C" int a1mpc_gen_schedule(int config_id, uint64_t stream, int B, int horizon, uint32_t* sched, double* normals) {
+  if (B <= 0 || horizon <= 0 || horizon > A1MPC_MAX_HORIZON || !sched || !normals) return A1MPC_EINVAL;
+  const uint64_t seed = 0x5C4ED0000ull + 0xA1C0FFEEull + (uint64_t)config_id + stream * 0x100000001B3ull;
+  const size_t ld = (size_t)B;
+  for (int b = 0; b < B; ++b) {
+    SplitMix64 rng(seed ^ ((uint64_t)(b + 1) * 0xD1342543DE82EF95ull));
+    const int gait = (int)(rng.next() % 3ull);       // 0 trot, 1 bound, 2 rotary gallop
+    const int phase0 = (int)(rng.next() % 16ull);
+    for (int st = 0; st < horizon; ++st) {
+      const int p = (phase0 + st) & 15;
+      uint32_t m;
+      if (gait == 0) m = (p < 8) ? 0b1001u : 0b0110u;            // {FL,RR} / {FR,RL}
+      else if (gait == 1) m = (p < 8) ? 0b0011u : 0b1100u;       // {FL,FR} / {RL,RR}
+      else {
+        const int off[4] = {0, 4, 12, 8};                          // FL, FR, RL, RR touch down a quarter period apart (rotary)
+        m = 0;
+        for (int leg = 0; leg < 4; ++leg)
+          if (((p + 16 - off[leg]) & 15) < 8) m |= 1u << leg;
+      }
+      sched[(size_t)st * ld + b] = m;
+    }
+    for (int leg = 0; leg < 4; ++leg) {
+      const double ang = rng.normal(0.2), az = rng.uniform(0.0, 6.283185307179586);
+      // rotate z by `ang` about the horizontal axis (cos az, sin az, 0)
+      const double ax = std::cos(az), ay = std::sin(az);
+      normals[(size_t)(3 * leg) * ld + b] = ay * std::sin(ang);
+      normals[(size_t)(3 * leg + 1) * ld + b] = -ax * std::sin(ang);
+      normals[(size_t)(3 * leg + 2) * ld + b] = std::cos(ang);
+    }
+  }
+  return A1MPC_OK;
+}

@@ -119,6 +119,19 @@ int  a1mpc_device_count(void);
  * pointers: enqueued on the handle's stream, asynchronous (use a1mpc_sync). */
 int  a1mpc_solve_batch(a1mpc_handle* h, int B, const a1mpc_inputs* in, const a1mpc_outputs* out);
 
+/* ---- BASELINE config 4: an EXTENSION beyond the reference (which keeps one contact pattern over the horizon,
+ * ConvexMpc.cpp:226-245, and world-z friction pyramids) ------------------------------------------------ */
+/*   contact_sched [N][B]  contact mask of every horizon step (batch-major, ld of `in`), or NULL = in->contact everywhere
+ *   normals       [12][B] terrain normal per foot (world frame, normalised by the engine), or NULL = world z.
+ * With normals the friction pyramid and the fz bounds act in each foot's terrain frame; the returned forces are
+ * world/body-frame as in a1mpc_solve_batch.  Restrictions: normals need r[3i] == r[3i+1] == r[3i+2] per foot (a rotated
+ * diagonal R would not be diagonal), normal z-components must be positive. */
+typedef struct a1mpc_inputs_ext {
+  const uint32_t* contact_sched;
+  const double*   normals;
+} a1mpc_inputs_ext;
+int  a1mpc_solve_batch_ext(a1mpc_handle* h, int B, const a1mpc_inputs* in, const a1mpc_inputs_ext* ext, const a1mpc_outputs* out);
+
 /* ---- ConvexMpc members, for parity with the reference class (ConvexMpc.h:87-93) ----------- */
 /* Dense QP data exactly as ConvexMpc::calculate_qp_mats leaves it after compute_grf drove it
  * (constant B_d over the horizon, A1RobotControl.cpp:498-514).  QP-major outputs:
@@ -201,6 +214,9 @@ int  a1mpc_allgather_forces(a1mpc_handle* h, const double* f_local, double* f_al
  * seed = 0xA1C0FFEE + config_id + `stream` (use the rank / batch index as stream). */
 int  a1mpc_gen_states(int config_id, uint64_t stream, int B, double* x0, double* rot, double* foot,
                       double* ref, uint32_t* contact);
+/* config-4 extras for the same (config_id, stream, B): per-step schedules [N][B] drawn from trot / bound / rotary gallop at
+ * a random phase of a 16-step period, and per-foot normals [12][B] = z tilted by N(0,0.2) rad about a random horizontal axis */
+int  a1mpc_gen_schedule(int config_id, uint64_t stream, int B, int horizon, uint32_t* contact_sched, double* normals);
 
 #ifdef __cplusplus
 }

@@ -912,15 +912,15 @@ static void kkt_certificate(int N, const Mat& P, const double* q, const double* 
   info->kkt_dual = (double)std::max(dual, (ld)0);
 }
 
-// exact solve of the literal MPC QP (P 12N x 12N, q, pyramid constraints with contact pattern)
-static bool exact_solve_literal(int N, const Mat& P, const double* q, const double* lbv, const double* ubv,
-                                const bool* contacts, double mu_f, double fzmin, double fzmax, double* x_out,
-                                ExactInfo* info) {
+// exact solve of the literal MPC QP (P 12N x 12N, q, pyramid constraints); step_masks[k] = contact mask of horizon step k
+static bool exact_solve_literal_sched(int N, const Mat& P, const double* q, const double* lbv, const double* ubv,
+                                      const uint32_t* step_masks, double mu_f, double fzmin, double fzmax, double* x_out,
+                                      ExactInfo* info) {
   const int nfull = 12 * N;
   std::vector<int> idx;
   for (int k = 0; k < N; ++k)
     for (int i = 0; i < 4; ++i)
-      if (contacts[i])
+      if ((step_masks[k] >> i) & 1u)
         for (int a = 0; a < 3; ++a) idx.push_back(12 * k + 3 * i + a);
   const int n = (int)idx.size();
   std::vector<ld> xfull(nfull, 0.0L);
@@ -939,6 +939,25 @@ static bool exact_solve_literal(int N, const Mat& P, const double* q, const doub
   kkt_certificate(N, P, q, lbv, ubv, mu_f, xfull, info);
   for (int i = 0; i < nfull; ++i) x_out[i] = (double)xfull[i];
   return ok;
+}
+static bool exact_solve_literal(int N, const Mat& P, const double* q, const double* lbv, const double* ubv,
+                                const bool* contacts, double mu_f, double fzmin, double fzmax, double* x_out,
+                                ExactInfo* info) {
+  uint32_t m = 0;
+  for (int i = 0; i < 4; ++i) m |= contacts[i] ? (1u << i) : 0u;
+  std::vector<uint32_t> masks(N, m);
+  return exact_solve_literal_sched(N, P, q, lbv, ubv, masks.data(), mu_f, fzmin, fzmax, x_out, info);
+}
+
+// rotation taking world z to the unit normal n (about the horizontal axis z x n); row-major 3x3
+static void terrain_frame(const double* n_in, double* R) {
+  double nx = n_in[0], ny = n_in[1], nz = n_in[2];
+  const double inv = 1.0 / std::sqrt(nx * nx + ny * ny + nz * nz);
+  nx *= inv; ny *= inv; nz *= inv;
+  const double k = 1.0 / (1.0 + nz);
+  R[0] = 1 - nx * nx * k; R[1] = -nx * ny * k;    R[2] = nx;
+  R[3] = -nx * ny * k;    R[4] = 1 - ny * ny * k; R[5] = ny;
+  R[6] = -nx;             R[7] = -ny;             R[8] = nz;
 }
 
 }  // namespace
@@ -1047,6 +1066,110 @@ int oracle_compute_grf_batch(const a1mpc_config* cfg, int B, const a1mpc_inputs*
     }
   };
   if (nthreads == 1) { work(); return 0; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t) th.emplace_back(work);
+  for (auto& t : th) t.join();
+  return 0;
+}
+
+// BASELINE config 4 (extension beyond the reference): per-step contact masks sched[N] and per-foot terrain normals (12) for
+// QP b.  The literal problem keeps all 12N world-frame forces; with normals the pyramid rows act on Rf^T f, which is the
+// same as solving for local forces with P' = Rb^T P Rb, q' = Rb^T q and the unrotated pyramid.
+static int solve_one_ext(const a1mpc_config* cfg, const a1mpc_inputs* in, int b, const uint32_t* sched, size_t sched_ld,
+                         const double* normals, size_t normals_ld, int mode, double* f_body, double* u_full, double* info8) {
+  const int N = cfg->horizon;
+  const int n = 12 * N, m = 20 * N;
+  RobotState st;
+  unpack(in, b, &st);
+  ConvexMpcRestated mpc(N, cfg->q, cfg->r, cfg->mu, cfg->fz_min, cfg->fz_max);
+  std::vector<double> x0, xd, sol(n, 0.0);
+  drive_convex_mpc(mpc, *cfg, st, x0, xd);
+  std::vector<uint32_t> masks(N);
+  for (int k = 0; k < N; ++k) masks[k] = (sched ? sched[(size_t)k * sched_ld + b] : in->contact[b]) & 15u;
+  for (int k = 0; k < N; ++k)
+    for (int i = 0; i < 4; ++i) {
+      const double c = ((masks[k] >> i) & 1u) ? 1.0 : 0.0;
+      mpc.lb[20 * k + 5 * i + 4] = cfg->fz_min * c;
+      mpc.ub[20 * k + 5 * i + 4] = cfg->fz_max * c;
+    }
+  double Rf[4][9];
+  for (int i = 0; i < 4; ++i) {
+    double nn[3] = {0, 0, 1};
+    if (normals)
+      for (int a = 0; a < 3; ++a) nn[a] = normals[(size_t)(3 * i + a) * normals_ld + b];
+    terrain_frame(nn, Rf[i]);
+  }
+  Mat P = mpc.hessian;
+  std::vector<double> q = mpc.gradient;
+  if (normals) {  // P' = Rb^T P Rb, q' = Rb^T q  (Rb = blockdiag of the foot frames, the same frame at every step)
+    Mat T(n, n);
+    for (int r = 0; r < n; ++r)
+      for (int kf = 0; kf < 4 * N; ++kf) {
+        const double* R = Rf[kf % 4];
+        for (int c2 = 0; c2 < 3; ++c2) {
+          double sacc = 0;
+          for (int a = 0; a < 3; ++a) sacc += mpc.hessian(r, 3 * kf + a) * R[3 * a + c2];
+          T(r, 3 * kf + c2) = sacc;
+        }
+      }
+    for (int kf = 0; kf < 4 * N; ++kf) {
+      const double* R = Rf[kf % 4];
+      for (int c2 = 0; c2 < 3; ++c2) {
+        for (int col = 0; col < n; ++col) {
+          double sacc = 0;
+          for (int a = 0; a < 3; ++a) sacc += R[3 * a + c2] * T(3 * kf + a, col);
+          P(3 * kf + c2, col) = sacc;
+        }
+        double sq = 0;
+        for (int a = 0; a < 3; ++a) sq += R[3 * a + c2] * mpc.gradient[3 * kf + a];
+        q[3 * kf + c2] = sq;
+      }
+    }
+  }
+  if (info8) std::fill(info8, info8 + 8, 0.0);
+  if (mode == ORACLE_MODE_EXACT) {
+    ExactInfo ei;
+    exact_solve_literal_sched(N, P, q.data(), mpc.lb.data(), mpc.ub.data(), masks.data(), cfg->mu, cfg->fz_min, cfg->fz_max, sol.data(), &ei);
+    if (info8) { info8[0] = ei.ipm_iters; info8[1] = ei.verified; info8[2] = ei.kkt_stat; info8[3] = ei.kkt_prim; info8[4] = ei.kkt_dual; info8[5] = ei.rounds; }
+  } else {
+    OsqpSettings os;
+    if (mode == ORACLE_MODE_OSQP_TIGHT) { os.eps_abs = os.eps_rel = 1e-11; os.max_iter = 400000; }
+    SparseRows A;
+    A.from_dense(mpc.linear_constraints);
+    OsqpInfo oi;
+    osqp_restated_solve(n, m, P, q.data(), A, mpc.lb.data(), mpc.ub.data(), os, sol.data(), &oi);
+    if (info8) { info8[0] = oi.iter; info8[1] = oi.status; }
+  }
+  // local -> world
+  std::vector<double> uw(n, 0.0);
+  for (int kf = 0; kf < 4 * N; ++kf) {
+    const double* R = Rf[kf % 4];
+    for (int a = 0; a < 3; ++a) uw[3 * kf + a] = R[3 * a] * sol[3 * kf] + R[3 * a + 1] * sol[3 * kf + 1] + R[3 * a + 2] * sol[3 * kf + 2];
+  }
+  if (f_body)
+    for (int i = 0; i < 4; ++i)
+      for (int a = 0; a < 3; ++a)
+        f_body[3 * i + a] = st.R[0 * 3 + a] * uw[3 * i] + st.R[1 * 3 + a] * uw[3 * i + 1] + st.R[2 * 3 + a] * uw[3 * i + 2];
+  if (u_full) std::memcpy(u_full, uw.data(), sizeof(double) * n);
+  return 0;
+}
+
+// sched [N][B] (ld = B) or NULL, normals [12][B] (ld = B) or NULL; outputs as oracle_compute_grf_batch
+int oracle_compute_grf_batch_ext(const a1mpc_config* cfg, int B, const a1mpc_inputs* in, const uint32_t* sched, const double* normals,
+                                 int mode, int nthreads, double* f_body, double* u_full, double* info) {
+  if (nthreads < 1) nthreads = 1;
+  const int n = 12 * cfg->horizon;
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    for (;;) {
+      int b = next.fetch_add(1);
+      if (b >= B) break;
+      double f[12];
+      solve_one_ext(cfg, in, b, sched, (size_t)B, normals, (size_t)B, mode, f, u_full ? u_full + (size_t)b * n : nullptr, info ? info + (size_t)b * 8 : nullptr);
+      if (f_body)
+        for (int k = 0; k < 12; ++k) f_body[(size_t)k * B + b] = f[k];
+    }
+  };
   std::vector<std::thread> th;
   for (int t = 0; t < nthreads; ++t) th.emplace_back(work);
   for (auto& t : th) t.join();

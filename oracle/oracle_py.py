@@ -114,6 +114,19 @@ def compute_grf_batch(cfg, batch, mode=MODE_EXACT, eps=0.0, nthreads=1, want_u=F
     return (f, info, u) if want_u else (f, info)
 
 
+def compute_grf_batch_ext(cfg, batch, sched=None, normals=None, mode=MODE_EXACT, nthreads=1, want_u=False):
+    """BASELINE config 4 (extension): per-step contact schedule [N,B] and/or terrain normals [12,B]"""
+    B = batch.B
+    f = np.zeros((12, B)); info = np.zeros((B, 8))
+    u = np.zeros((B, 12 * cfg.horizon)) if want_u else None
+    sc = np.ascontiguousarray(sched, dtype=np.uint32) if sched is not None else None
+    nm = np.ascontiguousarray(normals, dtype=np.float64) if normals is not None else None
+    inp = batch.c_inputs()
+    lib().oracle_compute_grf_batch_ext(C.byref(cfg), B, C.byref(inp), _ptr(sc) if sc is not None else None, _ptr(nm) if nm is not None else None,
+                                       mode, nthreads, _ptr(f), _ptr(u) if want_u else None, _ptr(info))
+    return (f, info, u) if want_u else (f, info)
+
+
 def solve_dense(cfg, H, g, contact, mode=MODE_EXACT):
     n = 12 * cfg.horizon
     u = np.zeros(n); info = np.zeros(8)

@@ -245,6 +245,42 @@ def test_grf_qp_branch(a1, O, gpu_engine):
         assert np.abs(f[b] - fo).max() <= TOL_F, (b, np.abs(f[b] - fo).max())
 
 
+def test_config4_contact_schedule_and_terrain_normals(a1, O, gpu_engine):
+    """BASELINE config 4 -- an extension beyond the reference: per-step contact schedules (trot / bound / rotary gallop at a
+    random phase), per-foot terrain normals, wide state noise.  Oracle = the restated literal problem generalised the same way
+    (per-step bounds, pyramid rows acting on Rf^T f), KKT-certified."""
+    B = 384
+    st = a1.gen_states(B, 4, 131)
+    sched, normals = a1.gen_schedule(B, 10, 4, 131)
+    sched[:, 0] = 0                      # no contact anywhere in the horizon
+    sched[:, 1] = 0b1111                 # all four feet all the time, tilted terrain only
+    sched[1:, 2] = 0                     # contact in the first step only
+    sched[0, 3] = 0                      # nobody in contact in the step whose force is returned
+    f, status, iters, u = gpu_engine.solve_ext(st, sched, normals, want_u=True)
+    fo, info, uo = O.compute_grf_batch_ext(O.make_config(), obatch(O, st), sched, normals, O.MODE_EXACT, nthreads=O.hardware_threads(), want_u=True)
+    assert (info[:, 1] == 1).all() and info[:, 2].max() <= 1e-12
+    assert status[0] == a1.STATUS_NO_CONTACT and np.abs(f[:, 0]).max() == 0
+    assert (status[1:] == a1.STATUS_OPTIMAL).all(), np.bincount(status)
+    assert np.abs(f - fo).max() <= TOL_F and np.abs(u.T - uo).max() <= TOL_F
+    assert np.abs(f[:, 3]).max() == 0
+    # schedule only / normals only / neither (falls through to the plain path)
+    f1, s1, _ = gpu_engine.solve_ext(st, sched, None)
+    fo1, _ = O.compute_grf_batch_ext(O.make_config(), obatch(O, st), sched, None, O.MODE_EXACT, nthreads=O.hardware_threads())
+    assert np.abs(f1 - fo1).max() <= TOL_F
+    f2, s2, _ = gpu_engine.solve_ext(st, None, normals)
+    fo2, _ = O.compute_grf_batch_ext(O.make_config(), obatch(O, st), None, normals, O.MODE_EXACT, nthreads=O.hardware_threads())
+    assert (s2 == 0).all() and np.abs(f2 - fo2).max() <= TOL_F
+    f3, s3, _ = gpu_engine.solve_ext(st, None, None)
+    f4, s4, _ = gpu_engine.solve(st)
+    assert np.array_equal(f3, f4)
+    # anisotropic r weights cannot be combined with tilted pyramids: loud error, not an approximation
+    wk = load_golden()["weights"]["hardware"]
+    eng = engine_for(a1, 10, wk)
+    with pytest.raises(a1.A1MpcError, match="isotropic"):
+        eng.solve_ext(st, None, normals)
+    eng.close()
+
+
 def test_joint_torques_next_row(a1, O, gpu_engine):
     """SURVEY 8f.1: A1RobotControl::compute_joint_torques (A1RobotControl.cpp:289-319), fed straight from the solver's forces"""
     B = 512

@@ -105,3 +105,24 @@ def test_grf_qp_single_two_methods(O):
     assert abs(f[2::3].sum() - acc[2]) < 1.0          # supports the weight (soft, Q_z = 100 vs R = 1e-3)
     f2, _ = O.grf_qp_single(acc, rot, rot, foot, 0b0101, O.MODE_EXACT)
     assert np.abs(f2[3:6]).max() == 0 and np.abs(f2[9:12]).max() == 0
+
+
+def test_config4_extension_oracle_two_methods(O, built):
+    """per-step contact schedule + terrain normals (extension beyond the reference): exact solver vs OSQP-algorithm run tight,
+    and the extension with nothing to extend equals the plain path"""
+    import a1mpc
+    B = 12
+    st = a1mpc.gen_states(B, 4, 5)
+    sched, normals = a1mpc.gen_schedule(B, 10, 4, 5)
+    assert sched.shape == (10, B) and np.abs(np.linalg.norm(normals.reshape(4, 3, B), axis=1) - 1).max() < 1e-14
+    cfg = O.make_config()
+    f, info = O.compute_grf_batch_ext(cfg, obatch(O, st), sched, normals, O.MODE_EXACT, nthreads=4)
+    ft, _ = O.compute_grf_batch_ext(cfg, obatch(O, st), sched, normals, O.MODE_OSQP_TIGHT, nthreads=4)
+    assert (info[:, 1] == 1).all() and info[:, 2].max() <= 1e-12 and info[:, 3].max() <= 1e-9 and info[:, 4].max() <= 1e-9
+    assert np.abs(f - ft).max() <= 1e-5
+    f0, _ = O.compute_grf_batch(cfg, obatch(O, st), O.MODE_EXACT)
+    f1, _ = O.compute_grf_batch_ext(cfg, obatch(O, st), None, None, O.MODE_EXACT)
+    assert np.abs(f0 - f1).max() <= 1e-12
+    # a foot that is in the air at step 0 gets exactly zero force
+    air = np.array([[((int(sched[0, b]) >> leg) & 1) == 0 for b in range(B)] for leg in range(4)])
+    assert np.abs(f.reshape(4, 3, B)[air.nonzero()[0], :, air.nonzero()[1]]).max() == 0
