@@ -18,7 +18,7 @@ STATUS_OPTIMAL, STATUS_IPM_ONLY, STATUS_MAXITER, STATUS_NUMERICAL, STATUS_NO_CON
 EXPORTS = [
     "a1mpc_default_config", "a1mpc_create", "a1mpc_destroy", "a1mpc_last_error", "a1mpc_device_count",
     "a1mpc_solve_batch", "a1mpc_solve_batch_ext", "a1mpc_build_qp_batch", "a1mpc_qp_mats_batch", "a1mpc_solve_dense_batch",
-    "a1mpc_grf_qp_batch", "a1mpc_joint_torques_batch", "a1mpc_device_alloc", "a1mpc_device_free", "a1mpc_host_alloc", "a1mpc_host_free",
+    "a1mpc_grf_qp_batch", "a1mpc_joint_torques_batch", "a1mpc_update_plan_batch", "a1mpc_device_alloc", "a1mpc_device_free", "a1mpc_host_alloc", "a1mpc_host_free",
     "a1mpc_memcpy_h2d", "a1mpc_memcpy_d2h", "a1mpc_sync", "a1mpc_event_create", "a1mpc_event_destroy",
     "a1mpc_event_record", "a1mpc_event_elapsed_ms", "a1mpc_launch_count", "a1mpc_measure_fp64_peak",
     "a1mpc_flush_l2", "a1mpc_profile_begin", "a1mpc_profile_end", "a1mpc_nccl_unique_id", "a1mpc_nccl_init", "a1mpc_allgather_forces", "a1mpc_gen_states", "a1mpc_gen_schedule",
@@ -36,6 +36,21 @@ class Config(C.Structure):
 class Inputs(C.Structure):
     _fields_ = [("x0", C.c_void_p), ("rot", C.c_void_p), ("foot", C.c_void_p), ("ref", C.c_void_p),
                 ("contact", C.c_void_p), ("ld", C.c_size_t)]
+
+
+class GaitParams(C.Structure):
+    _fields_ = [("counter_per_gait", C.c_double), ("counter_per_swing", C.c_double), ("control_dt", C.c_double),
+                ("default_foot_pos", C.c_double * 12), ("foot_delta_x_limit", C.c_double), ("foot_delta_y_limit", C.c_double),
+                ("horizon", C.c_int)]
+
+
+def default_gait_params(horizon=10):
+    """A1CtrlStates.h:23-24, 45-47, 332; A1Params.h:44-45"""
+    g = GaitParams()
+    g.counter_per_gait, g.counter_per_swing, g.control_dt = 240.0, 120.0, 0.0025
+    g.default_foot_pos[:] = [0.17, 0.17, -0.17, -0.17, 0.15, -0.15, 0.15, -0.15, -0.35, -0.35, -0.35, -0.35]
+    g.foot_delta_x_limit, g.foot_delta_y_limit, g.horizon = 0.1, 0.1, horizon
+    return g
 
 
 class InputsExt(C.Structure):
@@ -80,6 +95,7 @@ def lib():
         l.a1mpc_solve_dense_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
         l.a1mpc_grf_qp_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
         l.a1mpc_joint_torques_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
+        l.a1mpc_update_plan_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(GaitParams)] + [C.c_void_p] * 13
         l.a1mpc_gen_states.argtypes = [C.c_int, C.c_uint64, C.c_int] + [C.c_void_p] * 5
         l.a1mpc_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         l.a1mpc_profile_begin.argtypes = [C.c_void_p, C.c_int]
@@ -265,6 +281,19 @@ class Engine:
         tau = np.zeros((12, B)) if tau_prev is None else np.ascontiguousarray(tau_prev, dtype=np.float64).copy()
         _check(lib().a1mpc_joint_torques_batch(self.h, B, _p(a[0]), _p(a[1]), _p(a[2]), _p(contact), _p(a[3]), _p(a[4]), _p(tau)))
         return tau
+
+    def update_plan(self, gp, gait_counter, gait_counter_speed, movement_mode, lin_vel, lin_vel_d, rot_z, rot, root_pos):
+        """A1RobotControl::update_plan batched; returns new gait_counter [4,B], plan_contacts [B], contact_sched [N,B],
+        foot_pos_target_rel/abs/world [12,B]"""
+        gc = np.ascontiguousarray(gait_counter, dtype=np.float64).copy()
+        B = gc.shape[1]
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (gait_counter_speed, lin_vel, lin_vel_d, rot_z, rot, root_pos)]
+        mode = np.ascontiguousarray(movement_mode, dtype=np.uint32)
+        plan = np.zeros(B, dtype=np.uint32); sched = np.zeros((gp.horizon, B), dtype=np.uint32)
+        trel = np.zeros((12, B)); tabs = np.zeros((12, B)); tw = np.zeros((12, B))
+        _check(lib().a1mpc_update_plan_batch(self.h, B, C.byref(gp), _p(gc), _p(a[0]), _p(mode), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]),
+                                             _p(plan), _p(sched), _p(trel), _p(tabs), _p(tw)))
+        return gc, plan, sched, trel, tabs, tw
 
     # ---- memory / timing helpers ----
     def dalloc(self, nbytes):

@@ -577,6 +577,71 @@ int a1mpc_joint_torques_batch(a1mpc_handle* h, int B, const double* f_grf, const
   return A1MPC_OK;
 }
 
+int a1mpc_update_plan_batch(a1mpc_handle* h, int B, const a1mpc_gait_params* gp, double* gait_counter, const double* gait_counter_speed,
+                            const uint32_t* movement_mode, const double* lin_vel, const double* lin_vel_d, const double* rot_z,
+                            const double* rot, const double* root_pos, uint32_t* plan_contacts, uint32_t* contact_sched,
+                            double* t_rel, double* t_abs, double* t_world) {
+  if (!h || !gp || !gait_counter || !gait_counter_speed || !movement_mode || !plan_contacts) return fail(A1MPC_EINVAL, "null argument");
+  const bool want_t = t_rel || t_abs || t_world;
+  if (want_t && (!lin_vel || !lin_vel_d || !rot_z || !rot || !root_pos)) return fail(A1MPC_EINVAL, "foothold targets need lin_vel, lin_vel_d, rot_z, rot, root_pos");
+  if (B <= 0 || gp->horizon < 0 || gp->horizon > A1MPC_MAX_HORIZON) return fail(A1MPC_EINVAL, "bad B or horizon");
+  CK(cudaSetDevice(h->device));
+  GaitDev G;
+  G.cpg = gp->counter_per_gait; G.cps = gp->counter_per_swing; G.cdt = gp->control_dt; G.dxl = gp->foot_delta_x_limit; G.dyl = gp->foot_delta_y_limit;
+  for (int i = 0; i < 12; ++i) G.dfp[i] = gp->default_foot_pos[i];
+  G.N = gp->horizon;
+  const bool dev = is_device_ptr(gait_counter);
+  const size_t Bs = (size_t)B;
+  int rc;
+  if (dev) {
+    update_plan_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(B, G, gait_counter, gait_counter_speed, movement_mode, lin_vel, lin_vel_d, rot_z, rot, root_pos,
+                                                                plan_contacts, contact_sched, t_rel, t_abs, t_world);
+    h->launches++;
+    CK(cudaGetLastError());
+    return A1MPC_OK;
+  }
+  // host pointers: stage everything in one scratch allocation
+  const size_t nd = Bs * (4 + 4 + 3 + 3 + 9 + 9 + 3 + 36), nu = Bs * (1 + 1 + (size_t)G.N);
+  if ((rc = ensure_side(h, nd * 8 + nu * 4))) return rc;
+  double* p = (double*)h->d_side;
+  double* d_gc = p; p += 4 * Bs;
+  double* d_gcs = p; p += 4 * Bs;
+  double* d_lv = p; p += 3 * Bs;
+  double* d_lvd = p; p += 3 * Bs;
+  double* d_rz = p; p += 9 * Bs;
+  double* d_r = p; p += 9 * Bs;
+  double* d_pos = p; p += 3 * Bs;
+  double* d_trel = p; p += 12 * Bs;
+  double* d_tabs = p; p += 12 * Bs;
+  double* d_tw = p; p += 12 * Bs;
+  uint32_t* u = (uint32_t*)p;
+  uint32_t* d_mode = u; u += Bs;
+  uint32_t* d_plan = u; u += Bs;
+  uint32_t* d_sched = u;
+  CK(cudaMemcpyAsync(d_gc, gait_counter, 4 * Bs * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_gcs, gait_counter_speed, 4 * Bs * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_mode, movement_mode, Bs * 4, cudaMemcpyHostToDevice, h->stream));
+  if (want_t) {
+    CK(cudaMemcpyAsync(d_lv, lin_vel, 3 * Bs * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_lvd, lin_vel_d, 3 * Bs * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_rz, rot_z, 9 * Bs * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_r, rot, 9 * Bs * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_pos, root_pos, 3 * Bs * 8, cudaMemcpyHostToDevice, h->stream));
+  }
+  update_plan_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(B, G, d_gc, d_gcs, d_mode, d_lv, d_lvd, d_rz, d_r, d_pos, d_plan, contact_sched ? d_sched : nullptr,
+                                                              t_rel ? d_trel : nullptr, t_abs ? d_tabs : nullptr, t_world ? d_tw : nullptr);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(gait_counter, d_gc, 4 * Bs * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(plan_contacts, d_plan, Bs * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (contact_sched) CK(cudaMemcpyAsync(contact_sched, d_sched, (size_t)G.N * Bs * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (t_rel) CK(cudaMemcpyAsync(t_rel, d_trel, 12 * Bs * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (t_abs) CK(cudaMemcpyAsync(t_abs, d_tabs, 12 * Bs * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (t_world) CK(cudaMemcpyAsync(t_world, d_tw, 12 * Bs * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return A1MPC_OK;
+}
+
 // ---- helpers -------------------------------------------------------------------------------
 int a1mpc_device_alloc(a1mpc_handle* h, size_t bytes, void** ptr) {
   if (!h || !ptr) return fail(A1MPC_EINVAL, "null argument");

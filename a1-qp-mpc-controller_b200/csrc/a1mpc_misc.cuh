@@ -147,6 +147,67 @@ __global__ void joint_torques_kernel(int B, const double* __restrict__ f_grf, co
   }
 }
 
+// update_plan (A1RobotControl.cpp:148-202): thread per robot, batch-major coalesced.
+struct GaitDev { double cpg, cps, cdt, dfp[12], dxl, dyl; int N; };
+__global__ void update_plan_kernel(int B, GaitDev G, double* __restrict__ gc, const double* __restrict__ gcs, const uint32_t* __restrict__ mode,
+                                   const double* __restrict__ lv, const double* __restrict__ lvd, const double* __restrict__ rz,
+                                   const double* __restrict__ rot, const double* __restrict__ pos, uint32_t* __restrict__ plan,
+                                   uint32_t* __restrict__ sched, double* __restrict__ t_rel, double* __restrict__ t_abs, double* __restrict__ t_world) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const size_t ld = (size_t)B;
+  double c[4], sp[4];
+  uint32_t m = 0;
+  const bool walk = mode[b] != 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sp[i] = gcs[(size_t)i * ld + b];
+    if (!walk) {
+      c[i] = (i == 1 || i == 2) ? 120.0 : 0.0;   // gait_counter_reset(), trot
+      m |= 1u << i;
+    } else {
+      c[i] = fmod(gc[(size_t)i * ld + b] + sp[i], G.cpg);
+      if (c[i] <= G.cps) m |= 1u << i;
+    }
+    gc[(size_t)i * ld + b] = c[i];
+  }
+  plan[b] = m;
+  if (sched) {
+    for (int st = 0; st < G.N; ++st) {
+      uint32_t ms = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double ci = walk ? fmod(c[i] + (double)st * sp[i], G.cpg) : 0.0;
+        if (!walk || ci <= G.cps) ms |= 1u << i;
+      }
+      sched[(size_t)st * ld + b] = ms;
+    }
+  }
+  if (t_rel || t_abs || t_world) {
+    double v[3], vd[3], Rz[9], R[9], p[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { v[k] = lv[(size_t)k * ld + b]; vd[k] = lvd[(size_t)k * ld + b]; p[k] = pos[(size_t)k * ld + b]; }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { Rz[k] = rz[(size_t)k * ld + b]; R[k] = rot[(size_t)k * ld + b]; }
+    const double vr0 = Rz[0] * v[0] + Rz[3] * v[1] + Rz[6] * v[2], vr1 = Rz[1] * v[0] + Rz[4] * v[1] + Rz[7] * v[2];   // Rz^T v
+    const double kf = sqrt(fabs(G.dfp[8]) / 9.8);   // default_foot_pos(2): third scalar of the 3 x 4 matrix = z of leg 0
+    for (int i = 0; i < 4; ++i) {
+      double dx = kf * (vr0 - vd[0]) + ((G.cps / sp[i]) * G.cdt) / 2.0 * vd[0];
+      double dy = kf * (vr1 - vd[1]) + ((G.cps / sp[i]) * G.cdt) / 2.0 * vd[1];
+      dx = fmin(fmax(dx, -G.dxl), G.dxl);
+      dy = fmin(fmax(dy, -G.dyl), G.dyl);
+      const double f[3] = {G.dfp[0 * 4 + i] + dx, G.dfp[1 * 4 + i] + dy, G.dfp[2 * 4 + i]};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const double fa = R[3 * a] * f[0] + R[3 * a + 1] * f[1] + R[3 * a + 2] * f[2];
+        if (t_rel) t_rel[(size_t)(3 * i + a) * ld + b] = f[a];
+        if (t_abs) t_abs[(size_t)(3 * i + a) * ld + b] = fa;
+        if (t_world) t_world[(size_t)(3 * i + a) * ld + b] = fa + p[a];
+      }
+    }
+  }
+}
+
 // fp64 FMA pipe peak probe: 8 independent dependent-free DFMA chains per thread
 __global__ void fp64_peak_kernel(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;

@@ -176,6 +176,28 @@ int  a1mpc_grf_qp_batch(a1mpc_handle* h, int B, const double* root_acc, const do
 int  a1mpc_joint_torques_batch(a1mpc_handle* h, int B, const double* f_grf, const double* f_kin, const double* jac,
                                const uint32_t* contact, const double* km_foot, const double* torques_gravity, double* tau);
 
+/* ---- the step right before the path: A1RobotControl::update_plan ------------------------ */
+/* Gait counters -> planned contacts, and the Raibert foothold targets (A1RobotControl.cpp:148-202), batched; plus what the
+ * reference does not do: the planned contact mask of every horizon step (it freezes the current pattern,
+ * ConvexMpc.cpp:226-245), in the [N][B] layout a1mpc_solve_batch_ext takes.  Batch-major SoA (ld = B), host or device:
+ *   gait_counter [4][B] in/out; gait_counter_speed [4][B]; movement_mode [B] (0 standstill: all feet planned in contact and
+ *   the counters reset to the trot offsets 0,120,120,0 -- A1CtrlStates.h:322-326);
+ *   lin_vel [3][B] root_lin_vel (world); lin_vel_d [3][B] root_lin_vel_d; rot_z [9][B], rot [9][B], root_pos [3][B];
+ *   out: plan_contacts [B]; contact_sched [N][B] (step i = i plan ticks ahead; may be NULL);
+ *        foot_pos_target_rel / _abs / _world [12][B] leg-major (any may be NULL). */
+typedef struct a1mpc_gait_params {
+  double counter_per_gait;      /* 240  (A1CtrlStates.h:23)  */
+  double counter_per_swing;     /* 120  (A1CtrlStates.h:24)  */
+  double control_dt;            /* MAIN_UPDATE_FREQUENCY / 1000 (A1CtrlStates.h:332) */
+  double default_foot_pos[12];  /* 3 x NUM_LEG row-major (A1CtrlStates.h:45-47) */
+  double foot_delta_x_limit, foot_delta_y_limit;   /* A1Params.h:44-45 */
+  int    horizon;               /* steps of contact_sched */
+} a1mpc_gait_params;
+int  a1mpc_update_plan_batch(a1mpc_handle* h, int B, const a1mpc_gait_params* gp, double* gait_counter, const double* gait_counter_speed,
+                             const uint32_t* movement_mode, const double* lin_vel, const double* lin_vel_d, const double* rot_z,
+                             const double* rot, const double* root_pos, uint32_t* plan_contacts, uint32_t* contact_sched,
+                             double* foot_pos_target_rel, double* foot_pos_target_abs, double* foot_pos_target_world);
+
 /* ---- device memory, stream and timing helpers (so hosts need no CUDA headers) -------------- */
 int  a1mpc_device_alloc(a1mpc_handle* h, size_t bytes, void** ptr);
 int  a1mpc_device_free(a1mpc_handle* h, void* ptr);

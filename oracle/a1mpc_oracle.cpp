@@ -1326,6 +1326,59 @@ int oracle_joint_torques(const double* f_grf, const double* f_kin, const double*
   return 0;
 }
 
+// A1RobotControl::update_plan (A1RobotControl.cpp:148-202) for one robot; arrays as in the reference (3 x NUM_LEG row-major).
+// sched_out[N]: planned contact mask i ticks ahead (what update_plan would set after i more calls) -- the extension's input.
+int oracle_update_plan(double counter_per_gait, double counter_per_swing, double control_dt, const double* default_foot_pos,
+                       double dx_lim, double dy_lim, int movement_mode, double* gait_counter, const double* gait_counter_speed,
+                       const double* lin_vel, const double* lin_vel_d, const double* rot_z, const double* rot, const double* root_pos,
+                       int N, uint32_t* plan_contacts, uint32_t* sched_out, double* t_rel, double* t_abs, double* t_world) {
+  bool plan[4];
+  if (!movement_mode) {
+    for (int i = 0; i < 4; ++i) plan[i] = true;
+    gait_counter[0] = 0; gait_counter[1] = 120; gait_counter[2] = 120; gait_counter[3] = 0;
+  } else {
+    for (int i = 0; i < 4; ++i) {
+      gait_counter[i] = gait_counter[i] + gait_counter_speed[i];
+      gait_counter[i] = std::fmod(gait_counter[i], counter_per_gait);
+      plan[i] = gait_counter[i] <= counter_per_swing;
+    }
+  }
+  uint32_t m = 0;
+  for (int i = 0; i < 4; ++i) m |= plan[i] ? (1u << i) : 0u;
+  *plan_contacts = m;
+  // look-ahead: repeat the counter update i more times on a copy
+  double gc[4] = {gait_counter[0], gait_counter[1], gait_counter[2], gait_counter[3]};
+  for (int st = 0; st < N; ++st) {
+    uint32_t ms = 0;
+    for (int i = 0; i < 4; ++i) {
+      if (!movement_mode) { ms |= 1u << i; continue; }
+      if (st > 0) gc[i] = std::fmod(gc[i] + gait_counter_speed[i], counter_per_gait);
+      if (gc[i] <= counter_per_swing) ms |= 1u << i;
+    }
+    sched_out[st] = ms;
+  }
+  double vrel[3];
+  for (int a = 0; a < 3; ++a) vrel[a] = rot_z[0 * 3 + a] * lin_vel[0] + rot_z[1 * 3 + a] * lin_vel[1] + rot_z[2 * 3 + a] * lin_vel[2];
+  for (int i = 0; i < 4; ++i) {
+    double delta_x = std::sqrt(std::abs(default_foot_pos[2 * 4 + 0]) / 9.8) * (vrel[0] - lin_vel_d[0]) +
+                     ((counter_per_swing / gait_counter_speed[i]) * control_dt) / 2.0 * lin_vel_d[0];
+    double delta_y = std::sqrt(std::abs(default_foot_pos[2 * 4 + 0]) / 9.8) * (vrel[1] - lin_vel_d[1]) +
+                     ((counter_per_swing / gait_counter_speed[i]) * control_dt) / 2.0 * lin_vel_d[1];
+    if (delta_x < -dx_lim) delta_x = -dx_lim;
+    if (delta_x > dx_lim) delta_x = dx_lim;
+    if (delta_y < -dy_lim) delta_y = -dy_lim;
+    if (delta_y > dy_lim) delta_y = dy_lim;
+    double f[3] = {default_foot_pos[0 * 4 + i] + delta_x, default_foot_pos[1 * 4 + i] + delta_y, default_foot_pos[2 * 4 + i]};
+    for (int a = 0; a < 3; ++a) {
+      double fa = rot[3 * a] * f[0] + rot[3 * a + 1] * f[1] + rot[3 * a + 2] * f[2];
+      t_rel[3 * i + a] = f[a];
+      t_abs[3 * i + a] = fa;
+      t_world[3 * i + a] = fa + root_pos[a];
+    }
+  }
+  return 0;
+}
+
 // wall-clock timing of the reference-faithful path (build + OSQP default, cold start) on nthreads
 double oracle_time_reference_path(const a1mpc_config* cfg, int B, const a1mpc_inputs* in, int nthreads, double* f_body) {
   auto t0 = std::chrono::steady_clock::now();

@@ -150,6 +150,20 @@ def joint_torques(f_grf, f_kin, jac, contact, km_foot, torques_gravity, tau_prev
     return tau
 
 
+def update_plan(gp, movement_mode, gait_counter, gait_counter_speed, lin_vel, lin_vel_d, rot_z, rot, root_pos):
+    """one robot; gp = a1mpc.GaitParams-like (fields counter_per_gait, ..., horizon)"""
+    gc = np.array(gait_counter, dtype=np.float64)
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (gait_counter_speed, lin_vel, lin_vel_d, rot_z, rot, root_pos)]
+    dfp = np.array(list(gp.default_foot_pos), dtype=np.float64)
+    plan = C.c_uint32(); sched = np.zeros(gp.horizon, dtype=np.uint32)
+    trel = np.zeros(12); tabs = np.zeros(12); tw = np.zeros(12)
+    lib().oracle_update_plan(C.c_double(gp.counter_per_gait), C.c_double(gp.counter_per_swing), C.c_double(gp.control_dt), _ptr(dfp),
+                             C.c_double(gp.foot_delta_x_limit), C.c_double(gp.foot_delta_y_limit), int(movement_mode), _ptr(gc), _ptr(a[0]),
+                             _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), _ptr(a[4]), _ptr(a[5]), int(gp.horizon), C.byref(plan), _ptr(sched),
+                             _ptr(trel), _ptr(tabs), _ptr(tw))
+    return gc, int(plan.value), sched, trel, tabs, tw
+
+
 def time_reference_path(cfg, batch, nthreads):
     f = np.zeros((12, batch.B))
     inp = batch.c_inputs()

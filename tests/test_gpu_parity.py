@@ -300,6 +300,32 @@ def test_joint_torques_next_row(a1, O, gpu_engine):
     assert np.array_equal(tau[3:6, 7], prev[3:6, 7])      # swing leg 1 of robot 7: NaN force -> all three torques NaN -> kept
 
 
+def test_update_plan_previous_row(a1, O, gpu_engine):
+    """SURVEY 8f.2: A1RobotControl::update_plan (A1RobotControl.cpp:148-202) batched, plus the horizon contact schedule that the
+    extended solve consumes; then the schedule is actually fed to a1mpc_solve_batch_ext"""
+    B = 257
+    rng = np.random.default_rng(11)
+    st = a1.gen_states(B, 2, 141)
+    gp = a1.default_gait_params(10)
+    gc0 = rng.uniform(0, 240, (4, B)); gc0[:, 0] = [119.5, 239.0, 0.0, 120.0]
+    gcs = rng.choice([1.4, 1.5, 2.0], (4, B))
+    mode = (rng.uniform(size=B) < 0.8).astype(np.uint32)
+    yaw = st["x0"][2]
+    rot_z = np.stack([np.cos(yaw), -np.sin(yaw), 0 * yaw, np.sin(yaw), np.cos(yaw), 0 * yaw, 0 * yaw, 0 * yaw, 1 + 0 * yaw])
+    lvd = st["ref"][5:8].copy(); lvd[0, :5] = [2.0, -2.0, 0.0, 0.3, -0.3]     # saturates the foothold limits
+    gc, plan, sched, trel, tabs, tw = gpu_engine.update_plan(gp, gc0, gcs, mode, st["x0"][9:12], lvd, rot_z, st["rot"], st["x0"][3:6])
+    for b in range(B):
+        g1, p1, s1, r1, a1_, w1 = O.update_plan(gp, mode[b], gc0[:, b], gcs[:, b], st["x0"][9:12, b], lvd[:, b], rot_z[:, b], st["rot"][:, b], st["x0"][3:6, b])
+        assert np.array_equal(gc[:, b], g1) and plan[b] == p1 and np.array_equal(sched[:, b], s1), b
+        assert np.abs(trel[:, b] - r1).max() <= 1e-15 and np.abs(tabs[:, b] - a1_).max() <= 1e-15 and np.abs(tw[:, b] - w1).max() <= 1e-14
+    assert (sched[0] == plan).all()
+    f, status, _ = gpu_engine.solve_ext(st, sched, None)
+    fo, info = O.compute_grf_batch_ext(O.make_config(), obatch(O, st), sched, None, O.MODE_EXACT, nthreads=O.hardware_threads())
+    nocontact = (sched == 0).all(axis=0)          # random counters can put every foot in swing for the whole horizon
+    assert (status[nocontact] == a1.STATUS_NO_CONTACT).all() and (status[~nocontact] == 0).all()
+    assert np.abs(f - fo).max() <= TOL_F
+
+
 def test_fp64_peak_probe_and_profile_api(a1, gpu_engine):
     assert 20.0 < gpu_engine.fp64_peak_tflops() < 80.0     # B200 fp64 FMA pipe ~ 37-40 TFLOP/s
     st = a1.gen_states(512, 2, 111)
