@@ -67,6 +67,9 @@ struct a1mpc_handle {
   // NCCL (dlopen'ed)
   void* nccl_lib = nullptr;
   void* nccl_comm = nullptr;
+  cudaStream_t gather_stream = nullptr;   // the optional final collect runs here, overlapped with the next step's solve
+  cudaEvent_t ev_gather_in = nullptr, ev_gather_done = nullptr;
+  bool gather_pending = false;
 };
 
 namespace {
@@ -273,6 +276,7 @@ int a1mpc_destroy(a1mpc_handle* h) {
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
   }
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  if (h->gather_stream) { cudaStreamSynchronize(h->gather_stream); cudaStreamDestroy(h->gather_stream); cudaEventDestroy(h->ev_gather_in); cudaEventDestroy(h->ev_gather_done); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -678,9 +682,18 @@ int a1mpc_memcpy_d2h(a1mpc_handle* h, void* dst, const void* src, size_t bytes) 
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
   return A1MPC_OK;
 }
+static int join_gather(a1mpc_handle* h) {
+  if (h->gather_pending) {   // the compute stream (and everything timed on it) waits for the outstanding collect
+    CK(cudaStreamWaitEvent(h->stream, h->ev_gather_done, 0));
+    h->gather_pending = false;
+  }
+  return A1MPC_OK;
+}
+
 int a1mpc_sync(a1mpc_handle* h) {
   if (!h) return fail(A1MPC_EINVAL, "null argument");
   CK(cudaSetDevice(h->device));
+  { int rc = join_gather(h); if (rc) return rc; }
   CK(cudaStreamSynchronize(h->stream));
   return A1MPC_OK;
 }
@@ -700,6 +713,7 @@ int a1mpc_event_destroy(a1mpc_handle* h, void* ev) {
 int a1mpc_event_record(a1mpc_handle* h, void* ev) {
   if (!h || !ev) return fail(A1MPC_EINVAL, "null argument");
   CK(cudaSetDevice(h->device));
+  { int rc = join_gather(h); if (rc) return rc; }
   CK(cudaEventRecord((cudaEvent_t)ev, h->stream));
   return A1MPC_OK;
 }
@@ -788,6 +802,21 @@ int a1mpc_flush_l2(a1mpc_handle* h) {
 // accessors for a1mpc_nccl.cpp (which must not see the handle layout)
 extern "C" {
 void* a1mpc_internal_stream(a1mpc_handle* h) { return (void*)h->stream; }
+// forks the collect stream off the compute stream (everything enqueued so far is visible to the collective) and returns it
+void* a1mpc_internal_gather_begin(a1mpc_handle* h) {
+  if (!h->gather_stream) {
+    if (cudaStreamCreateWithFlags(&h->gather_stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&h->ev_gather_in, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_gather_done, cudaEventDisableTiming);
+  }
+  cudaEventRecord(h->ev_gather_in, h->stream);
+  cudaStreamWaitEvent(h->gather_stream, h->ev_gather_in, 0);
+  return (void*)h->gather_stream;
+}
+void a1mpc_internal_gather_end(a1mpc_handle* h) {
+  cudaEventRecord(h->ev_gather_done, h->gather_stream);
+  h->gather_pending = true;
+}
 int a1mpc_internal_device(a1mpc_handle* h) { return h->device; }
 void** a1mpc_internal_nccl_slot(a1mpc_handle* h) { return &h->nccl_comm; }
 void a1mpc_internal_set_error(const char* msg) { g_err = msg; }

@@ -12,6 +12,8 @@
 
 extern "C" {
 void* a1mpc_internal_stream(a1mpc_handle* h);
+void* a1mpc_internal_gather_begin(a1mpc_handle* h);
+void a1mpc_internal_gather_end(a1mpc_handle* h);
 int a1mpc_internal_device(a1mpc_handle* h);
 void** a1mpc_internal_nccl_slot(a1mpc_handle* h);
 void a1mpc_internal_set_error(const char* msg);
@@ -87,8 +89,13 @@ int a1mpc_allgather_forces(a1mpc_handle* h, const double* f_local, double* f_all
   if (!comm) { a1mpc_internal_set_error("a1mpc_nccl_init was not called"); return A1MPC_ENCCL; }
   cudaSetDevice(a1mpc_internal_device(h));
   // ncclFloat64 = 8
-  int rc = g.all_gather(f_local, f_all, (size_t)12 * B_local, 8, comm, (cudaStream_t)a1mpc_internal_stream(h));
+  // own stream, forked after the solve that produced f_local: the collect overlaps the next batch's kernels;
+  // a1mpc_sync / a1mpc_event_record join it back
+  void* gs = a1mpc_internal_gather_begin(h);
+  if (!gs) { a1mpc_internal_set_error("could not create the collect stream"); return A1MPC_ECUDA; }
+  int rc = g.all_gather(f_local, f_all, (size_t)12 * B_local, 8, comm, (cudaStream_t)gs);
   if (rc) return nccl_fail("ncclAllGather", rc);
+  a1mpc_internal_gather_end(h);
   return A1MPC_OK;
 }
 

@@ -227,7 +227,9 @@ int  a1mpc_flush_l2(a1mpc_handle* h);
  * library depends on it.  unique_id is a 128-byte ncclUniqueId produced on rank 0. */
 int  a1mpc_nccl_unique_id(void* unique_id128);
 int  a1mpc_nccl_init(a1mpc_handle* h, int nranks, int rank, const void* unique_id128);
-/* gathers f_local [12][B_local] (device) from every rank into f_all [nranks][12][B_local] */
+/* gathers f_local [12][B_local] (device) from every rank into f_all [nranks][12][B_local].  Asynchronous: the collective runs on
+ * the handle's collect stream after everything enqueued so far and overlaps later solves; a1mpc_sync and a1mpc_event_record
+ * wait for it.  Do not overwrite f_local / read f_all before one of them. */
 int  a1mpc_allgather_forces(a1mpc_handle* h, const double* f_local, double* f_all, int B_local);
 
 /* ---- synthetic workload generator, host-side, deterministic ------------------- */
