@@ -30,6 +30,7 @@ def test_struct_layout_matches_header(a1):
     # a1mpc_config: 2 ints, 5 doubles, 9+13+12 doubles, int (+pad), double
     assert C.sizeof(a1.Config) == 8 + 5 * 8 + 34 * 8 + 8 + 8
     assert C.sizeof(a1.Inputs) == 6 * 8 and C.sizeof(a1.Outputs) == 5 * 8
+    assert C.sizeof(a1.InputsExt) == 2 * 8 and C.sizeof(a1.GaitParams) == 3 * 8 + 12 * 8 + 2 * 8 + 8
 
 
 def test_default_config_is_the_launch_default(a1):

@@ -33,8 +33,12 @@ print("RANK_OK", rank)
 def test_two_rank_plumbing(tmp_path):
     script = tmp_path / "w.py"
     script.write_text(WORKER % (ROOT, ROOT))
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29617", CUDA_VISIBLE_DEVICES="")
+    import socket
+    with socket.socket() as sk:      # a free rendezvous port (back-to-back runs would otherwise collide in TIME_WAIT)
+        sk.bind(("127.0.0.1", 0))
+        port = str(sk.getsockname()[1])
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port, CUDA_VISIBLE_DEVICES="")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29617", str(script)], env=env, capture_output=True, text=True, timeout=300)
+                        "--master-port", port, str(script)], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "RANK_OK 0" in r.stdout and "RANK_OK 1" in r.stdout

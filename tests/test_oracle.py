@@ -126,3 +126,27 @@ def test_config4_extension_oracle_two_methods(O, built):
     # a foot that is in the air at step 0 gets exactly zero force
     air = np.array([[((int(sched[0, b]) >> leg) & 1) == 0 for b in range(B)] for leg in range(4)])
     assert np.abs(f.reshape(4, 3, B)[air.nonzero()[0], :, air.nonzero()[1]]).max() == 0
+
+
+def test_neighbour_rows_oracle_sanity(O):
+    """the restated update_plan / compute_joint_torques (the steps either side of the path) on hand-checkable inputs"""
+    import a1mpc
+    gp = a1mpc.default_gait_params(10)
+    eye = np.eye(3).ravel()
+    # standstill: all feet planned in contact, counters reset to the trot offsets (A1CtrlStates.h:322-326)
+    gc, plan, sched, trel, tabs, tw = O.update_plan(gp, 0, [5, 6, 7, 8], [2, 2, 2, 2], [0, 0, 0], [0, 0, 0], eye, eye, [0, 0, 0.3])
+    assert plan == 0b1111 and list(gc) == [0, 120, 120, 0] and (sched == 0b1111).all()
+    assert np.allclose(trel.reshape(4, 3), [[.17, .15, -.35], [.17, -.15, -.35], [-.17, .15, -.35], [-.17, -.15, -.35]])
+    assert np.allclose(tw.reshape(4, 3)[:, 2], -.35 + .3)
+    # walking: FL/RR half a cycle ahead of FR/RL; counters advance by their speed and wrap at counter_per_gait
+    gc, plan, sched, *_ = O.update_plan(gp, 1, [118, 238, 238, 118], [2, 2, 2, 2], [0, 0, 0], [0, 0, 0], eye, eye, [0, 0, 0.3])
+    assert list(gc) == [120, 0, 0, 120] and plan == 0b1111
+    assert sched[0] == 0b1111 and sched[1] == 0b0110 and (sched[1:] == 0b0110).all()      # FL, RR lift off one tick later
+    # Raibert foothold saturates at FOOT_DELTA_X_LIMIT
+    *_, trel, _, _ = O.update_plan(gp, 1, [0, 0, 0, 0], [2, 2, 2, 2], [5, 0, 0], [0, 0, 0], eye, eye, [0, 0, 0])
+    assert np.allclose(trel.reshape(4, 3)[:, 0], [.27, .27, -.07, -.07])
+    # torques: stance leg J^T(-f), swing leg J^-1 (km .* f_kin), + gravity compensation
+    jac = np.tile((2 * np.eye(3)).ravel(), 4)
+    f = np.arange(12.0); fk = np.ones(12) * 10
+    tau = O.joint_torques(f, fk, jac, 0b0001, [0.1, 0.1, 0.1], np.zeros(12))
+    assert np.allclose(tau[0:3], -2 * f[0:3]) and np.allclose(tau[3:], 0.5)
