@@ -26,7 +26,7 @@ dist.all_gather(out, t)
 assert not torch.equal(out[0], out[1])                   # shards differ
 assert torch.equal(out[rank], t)
 bench.dist_barrier(dist)
-print("RANK_OK", rank)
+sys.stdout.write("RANK_OK " + str(rank) + "\n"); sys.stdout.flush()    # one write per rank: the two ranks share a pipe
 '''
 
 
