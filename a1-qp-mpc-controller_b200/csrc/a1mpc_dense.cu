@@ -4,7 +4,11 @@
 //   * OsqpEigen::Solver replacement on a dense Hessian (A1RobotControl.cpp:522-555)
 //   * compute_grf's single-step QP branch (A1RobotControl.cpp:11-48, 377-445)
 // All three reuse the interior-point + finisher core of a1mpc_device.cuh through DenseHess.
+#ifndef A1MPC_EMU
 #include "a1mpc_internal.h"
+#else
+#include "a1mpc_device.cuh"   // tests/emu/ compiles the kernels of this file with g++ (test infrastructure)
+#endif
 
 namespace a1mpc {
 
@@ -17,7 +21,7 @@ template <int N>
 __global__ void __launch_bounds__(256) qp_mats_kernel(const __grid_constant__ DevParams P, int B, const double* __restrict__ A_d,
                                                       const double* __restrict__ B_list, const double* __restrict__ x0,
                                                       const double* __restrict__ x_d, double* __restrict__ H, double* __restrict__ g) {
-  extern __shared__ __align__(16) double sm[];
+  A1MPC_DYN_SMEM(sm);
   double* Apow = sm;                 // N x 169 : A_d^{k+1}
   double* W = Apow + N * 169;        // N x 13 x 12 : row block i of B_qp
   double* qe = W + N * 156;          // 13
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(32) dense_solve_kernel(const __grid_constant__
                                                          double* __restrict__ u, int32_t* __restrict__ status) {
   using G = Geo<NS, N>;
   using DG = DenseGeo<NS, N>;
-  extern __shared__ __align__(16) double smem[];
+  A1MPC_DYN_SMEM(smem);
   const int lane = threadIdx.x;
   Ctx<NS, N> c(smem + G::TAB_DOUBLES, smem, lane);
   double* Hs = smem + G::TAB_DOUBLES + G::WARP_DOUBLES;
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(32) grf_qp_kernel(const __grid_constant__ DevP
                                                     const int* __restrict__ list, const int* __restrict__ count,
                                                     double* __restrict__ f_body, int32_t* __restrict__ status) {
   using G = Geo<NS, 1>;
-  extern __shared__ __align__(16) double smem[];
+  A1MPC_DYN_SMEM(smem);
   const int lane = threadIdx.x;
   Ctx<NS, 1> c(smem + G::TAB_DOUBLES, smem, lane);
   double* Hs = smem + G::TAB_DOUBLES + G::WARP_DOUBLES;
@@ -327,6 +331,7 @@ __global__ void __launch_bounds__(32) grf_qp_kernel(const __grid_constant__ DevP
   }
 }
 
+#ifndef A1MPC_EMU
 // ------------------------------------------------------------------------------------------------
 // host wrappers
 // ------------------------------------------------------------------------------------------------
@@ -424,5 +429,7 @@ cudaError_t grf_qp_launch(int sm_count, int B, const double* root_acc, const dou
   if (nlaunch) *nlaunch = 5;
   return cudaGetLastError();
 }
+
+#endif  // A1MPC_EMU
 
 }  // namespace a1mpc

@@ -1,0 +1,188 @@
+// cuda_emu.h -- lane-accurate CPU emulation of one CUDA thread block.  TEST INFRASTRUCTURE ONLY.
+//
+// The device code of a1-qp-mpc-controller_b200/csrc/a1mpc_device.cuh is compiled UNCHANGED by g++ against this
+// shim (A1MPC_EMU) so that the warp-level algorithms (shuffles, ballots, DMMA fragments, shared-memory layouts) can be
+// checked against the oracle on a machine without a GPU.  It is not a CPU fallback: nothing in the product links it,
+// it is ~10^4 times slower than the GPU, and it exists only under tests/.
+//
+// Model: every CUDA thread is a fibre (own stack, hand-written context switch) on ONE host thread per block.  A fibre
+// runs until it reaches a warp collective (__shfl_sync, __any_sync, __syncwarp, mma, ...) or __syncthreads, publishes
+// its operand and yields; the last lane to arrive releases the warp.  Between two collectives the lanes of a warp run
+// one after the other in a configurable order (ascending / descending / pseudo-random): code that relies on implicit
+// lock-step (a missing __syncwarp around shared memory) gives order-dependent results, which the tests detect by
+// comparing the orders bit for bit.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+#define __device__
+#define __global__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
+#define __launch_bounds__(...)
+#define __grid_constant__
+#define __align__(n) alignas(n)
+#define __shared__ static thread_local   // one block per host thread at a time: shared by all fibres of the block
+
+namespace a1emu {
+
+struct Dim3 { unsigned x = 1, y = 1, z = 1; };
+
+struct Fiber {
+  void* sp = nullptr;
+  char* stack = nullptr;
+  bool done = false;
+};
+
+struct Warp {
+  unsigned gen = 0;
+  int count = 0, nlanes = 32;
+  uint64_t slot[2][32];
+  uint64_t slot2[2][32];
+};
+
+struct Block {
+  int nthreads = 0;
+  std::vector<Fiber> fib;
+  std::vector<Warp> warps;
+  unsigned bgen = 0;
+  int bcount = 0;
+  void* sched_sp = nullptr;
+  int cur = 0;
+  unsigned long progress = 0;
+  std::function<void()> body;
+  std::vector<double> smem;
+  int order_mode = 0;       // 0 ascending, 1 descending, 2 pseudo-random
+  uint64_t rng = 0x9E3779B97F4A7C15ull;
+  unsigned long n_collectives = 0, n_mma = 0;
+};
+
+extern thread_local Block* g_blk;
+void yield_to_scheduler();
+// runs `body` once per thread of one block (threadIdx/blockDim set), with dynamic shared memory of smem_bytes
+void run_block(Dim3 block_idx, Dim3 grid_dim, int nthreads, size_t smem_bytes, int order_mode, const std::function<void()>& body,
+               unsigned long* n_collectives = nullptr, unsigned long* n_mma = nullptr);
+
+}  // namespace a1emu
+
+extern thread_local a1emu::Dim3 threadIdx, blockIdx, blockDim, gridDim;
+
+namespace a1emu {
+
+inline int lane_id() { return (int)(threadIdx.x & 31u); }
+inline Warp& my_warp() { return g_blk->warps[threadIdx.x >> 5]; }
+
+// publish (v, v2), wait for the whole warp, return the generation whose slots hold this collective's operands
+inline unsigned warp_arrive(uint64_t v, uint64_t v2 = 0) {
+  Warp& w = my_warp();
+  const unsigned g = w.gen;
+  const int lane = lane_id();
+  w.slot[g & 1][lane] = v;
+  w.slot2[g & 1][lane] = v2;
+  if (++w.count == w.nlanes) {
+    w.count = 0;
+    w.gen = g + 1;
+    ++g_blk->progress;
+    ++g_blk->n_collectives;
+  } else {
+    while (w.gen == g) yield_to_scheduler();
+  }
+  return g;
+}
+
+inline uint64_t d2u(double x) { uint64_t u; std::memcpy(&u, &x, 8); return u; }
+inline double u2d(uint64_t u) { double x; std::memcpy(&x, &u, 8); return x; }
+
+}  // namespace a1emu
+
+// ------------------------------------------------------------------------------------------------
+// warp collectives (full-mask forms only: that is all the device code uses)
+// ------------------------------------------------------------------------------------------------
+inline void __syncwarp(unsigned = 0xffffffffu) { a1emu::warp_arrive(0); }
+inline double __shfl_sync(unsigned, double v, int src) {
+  a1emu::Warp& w = a1emu::my_warp();
+  const unsigned g = a1emu::warp_arrive(a1emu::d2u(v));
+  return a1emu::u2d(w.slot[g & 1][src & 31]);
+}
+inline int __shfl_sync(unsigned, int v, int src) {
+  a1emu::Warp& w = a1emu::my_warp();
+  const unsigned g = a1emu::warp_arrive((uint64_t)(uint32_t)v);
+  return (int)(uint32_t)w.slot[g & 1][src & 31];
+}
+inline double __shfl_xor_sync(unsigned m, double v, int x) { return __shfl_sync(m, v, a1emu::lane_id() ^ x); }
+inline int __shfl_xor_sync(unsigned m, int v, int x) { return __shfl_sync(m, v, a1emu::lane_id() ^ x); }
+inline unsigned __ballot_sync(unsigned, int pred) {
+  a1emu::Warp& w = a1emu::my_warp();
+  const unsigned g = a1emu::warp_arrive(pred ? 1u : 0u);
+  unsigned m = 0;
+  for (int l = 0; l < 32; ++l) m |= (w.slot[g & 1][l] ? 1u : 0u) << l;
+  return m;
+}
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
+inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
+inline int __reduce_add_sync(unsigned, int v) {
+  a1emu::Warp& w = a1emu::my_warp();
+  const unsigned g = a1emu::warp_arrive((uint64_t)(uint32_t)v);
+  int s = 0;
+  for (int l = 0; l < 32; ++l) s += (int)(uint32_t)w.slot[g & 1][l];
+  return s;
+}
+inline void __syncthreads() {
+  a1emu::Block& b = *a1emu::g_blk;
+  const unsigned g = b.bgen;
+  if (++b.bcount == b.nthreads) {
+    b.bcount = 0;
+    b.bgen = g + 1;
+    ++b.progress;
+  } else {
+    while (b.bgen == g) a1emu::yield_to_scheduler();
+  }
+}
+
+// mma.sync.aligned.m8n8k4.row.col.f64 (PTX ISA fragment layout): A: lane l holds A[l>>2][l&3]; B: lane l holds
+// B[l&3][l>>2]; C/D: lane l holds [l>>2][2(l&3)], [l>>2][2(l&3)+1].
+inline void a1emu_dmma884(double& d0, double& d1, double a, double b, double c0, double c1) {
+  a1emu::Warp& w = a1emu::my_warp();
+  const unsigned g = a1emu::warp_arrive(a1emu::d2u(a), a1emu::d2u(b));
+  ++a1emu::g_blk->n_mma;
+  const int lane = a1emu::lane_id(), row = lane >> 2, col = 2 * (lane & 3);
+  double r0 = c0, r1 = c1;
+  for (int k = 0; k < 4; ++k) {
+    const double av = a1emu::u2d(w.slot[g & 1][row * 4 + k]);
+    r0 = std::fma(av, a1emu::u2d(w.slot2[g & 1][col * 4 + k]), r0);
+    r1 = std::fma(av, a1emu::u2d(w.slot2[g & 1][(col + 1) * 4 + k]), r1);
+  }
+  // the operands of this collective stay valid until every lane has arrived at the NEXT one, so no second barrier
+  d0 = r0;
+  d1 = r1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scalar intrinsics
+// ------------------------------------------------------------------------------------------------
+using std::fabs;
+using std::fma;
+using std::fmax;
+using std::fmin;
+using std::max;
+using std::min;
+using std::sqrt;
+inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+inline double __drcp_rn(double x) { return 1.0 / x; }
+inline double __dsqrt_rn(double x) { return std::sqrt(x); }
+inline int __double2hiint(double x) { return (int)(uint32_t)(a1emu::d2u(x) >> 32); }
+inline int __double2loint(double x) { return (int)(uint32_t)(a1emu::d2u(x) & 0xffffffffull); }
+inline long long __double_as_longlong(double x) { return (long long)a1emu::d2u(x); }
+inline double __longlong_as_double(long long x) { return a1emu::u2d((uint64_t)x); }
+inline double __hiloint2double(int hi, int lo) { return a1emu::u2d(((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo); }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }

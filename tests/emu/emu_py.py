@@ -1,0 +1,68 @@
+"""ctypes binding of the CPU block emulator (tests/emu/liba1mpc_emu.so).  TEST INFRASTRUCTURE: the device code of
+a1mpc_device.cuh compiled by g++ against a lane-accurate emulation of the warp primitives (cuda_emu.h)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(_HERE))
+sys.path.insert(0, os.path.join(ROOT, "a1-qp-mpc-controller_b200"))
+import a1mpc  # noqa: E402  (struct definitions only; the emulator never touches liba1mpc.so)
+
+_LIB = None
+
+
+def lib(flags=""):
+    global _LIB
+    if _LIB is None:
+        env = dict(os.environ)
+        if flags:
+            env["EMUFLAGS"] = flags
+        subprocess.check_call(["make", "-C", _HERE, "-s"], env=env)
+        _LIB = C.CDLL(os.path.join(_HERE, "liba1mpc_emu.so"))
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def solve(cfg, st, sched=None, normals=None, order=0, nthreads=8, want_u=False):
+    """st: dict x0[12,B] rot[9,B] foot[12,B] ref[9,B] contact[B]; returns f_body[12,B], status[B], iters[B] (, u_full), stats"""
+    B = st["contact"].shape[0]
+    arrs = [np.ascontiguousarray(st[k], dtype=np.float64) for k in ("x0", "rot", "foot", "ref")]
+    contact = np.ascontiguousarray(st["contact"], dtype=np.uint32)
+    inp = a1mpc.Inputs(_p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(contact), B)
+    f = np.zeros((12, B)); status = np.full(B, -7, dtype=np.int32); iters = np.zeros(B, dtype=np.int32)
+    u = np.zeros((12 * cfg.horizon, B)) if want_u else None
+    out = a1mpc.Outputs(_p(f), _p(status), _p(iters), _p(u), B)
+    sc = np.ascontiguousarray(sched, dtype=np.uint32) if sched is not None else None
+    nm = np.ascontiguousarray(normals, dtype=np.float64) if normals is not None else None
+    stats = (C.c_ulong * 2)()
+    rc = lib().emu_solve_batch(C.byref(cfg), B, C.byref(inp), _p(sc), _p(nm), C.byref(out), order, nthreads, stats)
+    assert rc == 0
+    res = (f, status, iters) + ((u,) if want_u else ())
+    return res + ({"collectives": int(stats[0]), "mma": int(stats[1])},)
+
+
+def solve_dense(cfg, H, g, contact, order=0):
+    """H [B,n,n], g [B,n], contact [B] -> u [B,n], status [B]  (a1mpc_solve_dense_batch on the emulator, N = 10)"""
+    H = np.ascontiguousarray(H, dtype=np.float64); g = np.ascontiguousarray(g, dtype=np.float64)
+    contact = np.ascontiguousarray(contact, dtype=np.uint32)
+    B, n = g.shape
+    u = np.zeros((B, n)); status = np.full(B, -7, dtype=np.int32)
+    assert lib().emu_solve_dense(C.byref(cfg), B, _p(H), _p(g), _p(contact), _p(u), _p(status), order) == 0
+    return u, status
+
+
+def grf_qp(root_acc, rot_z, rot, foot, contact, order=0):
+    """a1mpc_grf_qp_batch on the emulator: root_acc [B,6], rot_z/rot [B,9], foot [B,12], contact [B] -> f_body [B,12], status"""
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (root_acc, rot_z, rot, foot)]
+    contact = np.ascontiguousarray(contact, dtype=np.uint32)
+    B = contact.shape[0]
+    f = np.zeros((B, 12)); status = np.full(B, -7, dtype=np.int32)
+    assert lib().emu_grf_qp(B, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(contact), _p(f), _p(status), order) == 0
+    return f, status

@@ -1,0 +1,121 @@
+"""The device code of a1mpc_device.cuh on the lane-accurate CPU emulator (tests/emu/) against the oracle.
+
+Test infrastructure, not a product path: the SAME kernels nvcc compiles for sm_100a are compiled by g++ against an
+emulation of the warp primitives (shuffles, ballots, mma.m8n8k4.f64 fragments, __syncwarp) and run one fibre per CUDA
+thread.  This catches, without a GPU, what the oracle alone cannot: wrong fragment/lane maps, wrong shared-memory tile
+addressing, missing barriers (results must not depend on the order in which the lanes of a warp run between two
+collectives), misaligned 128-bit shared accesses.  The GPU parity tests (-m gpu) remain the gate for the real thing."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+from common import obatch  # noqa: E402
+
+TOL_F = 1e-4   # N, the gate of the GPU parity tests
+
+
+@pytest.fixture(scope="module")
+def E():
+    import emu_py
+    emu_py.lib()
+    return emu_py
+
+
+@pytest.fixture(scope="module")
+def a1(E):
+    return E.a1mpc
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle_py
+    oracle_py.lib()
+    return oracle_py
+
+
+def _mixed_states(a1, B, config_id, stream):
+    st = a1.gen_states(B, config_id, stream)
+    pats = [1, 2, 4, 8, 3, 5, 6, 9, 10, 12, 7, 11, 13, 14, 15, 0]
+    for i in range(min(B, len(pats))):
+        st["contact"][i] = pats[i]
+    return st
+
+
+@pytest.mark.parametrize("horizon,B", [(10, 96), (20, 24)])
+def test_fused_kernels_on_emulator_match_oracle(E, a1, O, horizon, B):
+    cfg = a1.default_config(horizon=horizon)
+    st = _mixed_states(a1, B, 2, 17)
+    f, status, iters, u, stats = E.solve(cfg, st, order=0, want_u=True)
+    assert stats["collectives"] > 0
+    fo, info, uo = O.compute_grf_batch(O.make_config(horizon=horizon), obatch(O, st), mode=O.MODE_EXACT, nthreads=4, want_u=True)
+    nc = st["contact"] == 0
+    assert (status[nc] == a1.STATUS_NO_CONTACT).all() and (status[~nc] == a1.STATUS_OPTIMAL).all()
+    assert np.abs(f - fo).max() <= TOL_F and np.abs(f - fo).max() < 1e-6
+    assert np.abs(u - uo.T).max() <= TOL_F
+
+
+def test_lane_order_between_collectives_does_not_matter(E, a1):
+    """a missing __syncwarp around shared memory shows up as an order-dependent result"""
+    cfg = a1.default_config(horizon=10)
+    st = _mixed_states(a1, 48, 2, 23)
+    ref = E.solve(cfg, st, order=0, want_u=True)
+    for order in (1, 2):
+        got = E.solve(cfg, st, order=order, want_u=True)
+        assert np.array_equal(ref[0], got[0]) and np.array_equal(ref[1], got[1]) and np.array_equal(ref[2], got[2])
+        assert np.array_equal(ref[3], got[3])
+
+
+def test_config4_schedules_and_normals_on_emulator(E, a1, O):
+    B = 40
+    st = a1.gen_states(B, 4, 131)
+    sched, normals = a1.gen_schedule(B, 10, 4, 131)
+    cfg = a1.default_config(horizon=10)
+    f, status, iters, stats = E.solve(cfg, st, sched=sched, normals=normals, order=2)
+    fo, info = O.compute_grf_batch_ext(O.make_config(horizon=10), obatch(O, st), sched, normals, mode=O.MODE_EXACT, nthreads=4)
+    assert (status == a1.STATUS_OPTIMAL).all()
+    assert np.abs(f - fo).max() <= TOL_F
+
+
+def test_dense_solve_on_emulator(E, a1, O):
+    B = 10
+    st = a1.gen_states(B, 4, 91)
+    st["contact"][:6] = [0b0001, 0b0111, 0b1111, 0b0110, 0b1000, 0]
+    cfg = a1.default_config(horizon=10)
+    ocfg = O.make_config()
+    ob = obatch(O, st)
+    Hg = [O.build_qp(ocfg, ob, b) for b in range(B)]
+    H = np.stack([x[0] for x in Hg]); g = np.stack([x[1] for x in Hg])
+    u, status = E.solve_dense(cfg, H, g, st["contact"], order=1)
+    for b in range(B):
+        if st["contact"][b] == 0:
+            assert status[b] == a1.STATUS_NO_CONTACT and np.abs(u[b]).max() == 0
+            continue
+        uo, info = O.solve_dense(ocfg, H[b], g[b], st["contact"][b], O.MODE_EXACT)
+        assert status[b] == 0 and np.abs(u[b] - uo).max() <= TOL_F, (b, status[b])
+
+
+def test_grf_qp_on_emulator(E, a1, O):
+    rng = np.random.default_rng(5)
+    B = 24
+    st = a1.gen_states(B, 2, 101)
+    rot = st["rot"].T.copy()
+    yaw = st["x0"][2]
+    rot_z = np.stack([np.cos(yaw), -np.sin(yaw), 0 * yaw, np.sin(yaw), np.cos(yaw), 0 * yaw, 0 * yaw, 0 * yaw, 1 + 0 * yaw], axis=1)
+    foot = st["foot"].T.copy()
+    acc = np.stack([rng.normal(0, 20, B), rng.normal(0, 20, B), 12 * 9.8 + rng.normal(0, 30, B), rng.normal(0, 5, B), rng.normal(0, 5, B),
+                    rng.normal(0, 2, B)], axis=1)
+    contact = st["contact"].copy()
+    contact[:6] = [0b1111, 0b0001, 0b0111, 0, 0b1010, 0b1111]
+    acc[5] = [400, -300, 2500, 50, -40, 10]
+    f, status = E.grf_qp(acc, rot_z, rot, foot, contact, order=2)
+    for b in range(B):
+        if contact[b] == 0:
+            assert status[b] == a1.STATUS_NO_CONTACT and np.abs(f[b]).max() == 0
+            continue
+        fo, info = O.grf_qp_single(acc[b], rot_z[b], rot[b], foot[b], contact[b], O.MODE_EXACT)
+        assert status[b] == 0 and np.abs(f[b] - fo).max() <= TOL_F, (b, status[b])
