@@ -3,10 +3,11 @@ NVCC ?= /usr/local/cuda/bin/nvcc
 CXX ?= g++
 PKG := a1-qp-mpc-controller_b200
 SRC := $(PKG)/csrc
-OBJ := build
+OBJ ?= build
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr
-LIB := $(PKG)/liba1mpc.so
+EXTRA ?=
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr $(EXTRA)
+LIB ?= $(PKG)/liba1mpc.so
 
 CU := a1mpc_api a1mpc_solve_n10 a1mpc_solve_n20 a1mpc_solve_ext a1mpc_build a1mpc_dense
 CPP := a1mpc_gen a1mpc_nccl

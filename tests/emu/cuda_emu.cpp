@@ -53,7 +53,14 @@ void run_block(Dim3 block_idx, Dim3 grid_dim, int nthreads, size_t smem_bytes, i
   b.nthreads = nthreads;
   b.body = body;
   b.order_mode = order_mode;
-  b.smem.assign(smem_bytes / 8 + 2, 0.0);
+  // shared memory is NOT zero on a GPU: poison it (NaN) so that any read of a never-written word shows up in the results
+  static const bool poison = std::getenv("A1EMU_NO_POISON") == nullptr;
+  b.smem.assign(smem_bytes / 8 + 2, poison ? std::nan("") : 0.0);
+  if (const char* r = std::getenv("A1EMU_POISON_RANGE")) {   // debugging aid: "lo:hi" (doubles) -- poison only that window
+    long lo = 0, hi = 0;
+    if (std::sscanf(r, "%ld:%ld", &lo, &hi) == 2)
+      for (long i = 0; i < (long)b.smem.size(); ++i) b.smem[i] = (i >= lo && i < hi) ? std::nan("") : 0.0;
+  }
   b.fib.resize(nthreads);
   b.warps.resize((nthreads + 31) / 32);
   for (size_t w = 0; w < b.warps.size(); ++w) b.warps[w].nlanes = std::min(32, nthreads - 32 * (int)w);
