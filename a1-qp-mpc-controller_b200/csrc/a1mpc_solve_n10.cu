@@ -34,17 +34,17 @@ static void launch_one(const ClassLaunch& c, cudaStream_t st, int B, const DevPa
 #if A1MPC_HORIZON == 10
 cudaError_t fused_setup_n10(int sm_count, ClassLaunch (&cls)[5]) {
   cudaError_t e;
-  if ((e = setup_one<1, 10, 4, 0>(sm_count, cls[1])) != cudaSuccess) return e;
-  if ((e = setup_one<2, 10, 2, 0>(sm_count, cls[2])) != cudaSuccess) return e;
-  if ((e = setup_one<3, 10, 1, 1>(sm_count, cls[3])) != cudaSuccess) return e;
-  if ((e = setup_one<4, 10, 1, 1>(sm_count, cls[4])) != cudaSuccess) return e;
+  if ((e = setup_one<1, 10, A1MPC_WPC1, 0>(sm_count, cls[1])) != cudaSuccess) return e;
+  if ((e = setup_one<2, 10, A1MPC_WPC2, 0>(sm_count, cls[2])) != cudaSuccess) return e;
+  if ((e = setup_one<3, 10, A1MPC_WPC34, 1>(sm_count, cls[3])) != cudaSuccess) return e;
+  if ((e = setup_one<4, 10, A1MPC_WPC34, 1>(sm_count, cls[4])) != cudaSuccess) return e;
   return cudaSuccess;
 }
 void fused_launch_n10(int ns, const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count, const DevOutputs& out) {
-  if (ns == 1) launch_one<1, 10, 4, 0>(c, st, B, P, rec, count, out);
-  if (ns == 2) launch_one<2, 10, 2, 0>(c, st, B, P, rec, count, out);
-  if (ns == 3) launch_one<3, 10, 1, 1>(c, st, B, P, rec, count, out);
-  if (ns == 4) launch_one<4, 10, 1, 1>(c, st, B, P, rec, count, out);
+  if (ns == 1) launch_one<1, 10, A1MPC_WPC1, 0>(c, st, B, P, rec, count, out);
+  if (ns == 2) launch_one<2, 10, A1MPC_WPC2, 0>(c, st, B, P, rec, count, out);
+  if (ns == 3) launch_one<3, 10, A1MPC_WPC34, 1>(c, st, B, P, rec, count, out);
+  if (ns == 4) launch_one<4, 10, A1MPC_WPC34, 1>(c, st, B, P, rec, count, out);
 }
 #else
 cudaError_t fused_setup_n20(int sm_count, ClassLaunch (&cls)[5]) {

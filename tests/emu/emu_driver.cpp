@@ -34,7 +34,7 @@ void run_class(const DevParams& P, const double* rec, const int* count, const De
   using G = Geo<NS, N, LSM>;
   const int nq = count[EXT ? 5 : NS];
   if (nq == 0) return;
-  const int grid = (nq + WPC - 1) / WPC;
+  const int grid = std::max(1, (nq + 2 * WPC - 1) / (2 * WPC));   // ~2 QPs per warp: exercises the persistent loop (and the CTA rendezvous)
   std::atomic<int> next{0};
   auto worker = [&]() {
     for (;;) {
@@ -57,10 +57,10 @@ template <int N>
 void run_all(const DevParams& P, const double* rec, size_t cap, const int* count, const DevOutputs& out, int order_mode, int nthreads, Stats& st);
 template <>
 void run_all<10>(const DevParams& P, const double* rec, size_t cap, const int* count, const DevOutputs& out, int order_mode, int nthreads, Stats& st) {
-  run_class<1, 10, 4, 0, false>(P, rec + 0 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st);
-  run_class<2, 10, 2, 0, false>(P, rec + 1 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st);
-  run_class<3, 10, 1, 1, false>(P, rec + 2 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st);
-  run_class<4, 10, 1, 1, false>(P, rec + 3 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st);
+  run_class<1, 10, A1MPC_WPC1, 0, false>(P, rec + 0 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st);
+  run_class<2, 10, A1MPC_WPC2, 0, false>(P, rec + 1 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st);
+  run_class<3, 10, A1MPC_WPC34, 1, false>(P, rec + 2 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st);
+  run_class<4, 10, A1MPC_WPC34, 1, false>(P, rec + 3 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st);
 }
 template <>
 void run_all<20>(const DevParams& P, const double* rec, size_t cap, const int* count, const DevOutputs& out, int order_mode, int nthreads, Stats& st) {
