@@ -374,7 +374,7 @@ def main():
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_qp": ALG_BYTES_PER_QP, "qps_per_launch": dom_qps, "kernel_ms": dom_ms,
                 "note": "the path is fp64-pipe/latency bound (SURVEY 8d: ~1e4 FLOP/B), so the HBM fraction is small by construction; see roofline_fp64"}
-    roofline_fp64 = {"bound": "fp64-fma-pipe", "kernel": roofline["kernel"], "unit": "TFLOP/s",
+    roofline_fp64 = {"bound": "fp64 pipes (DFMA + DMMA.8x8x4; the tensor and the vector fp64 peak of a B200 are about equal)", "kernel": roofline["kernel"], "unit": "TFLOP/s",
                      "achieved_algorithmic": fl_alg / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0,
                      "achieved_executed": fl_exec / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0,
                      "peak": fp64_peak, "peak_source": "measured in this run (a1mpc_measure_fp64_peak: dependent-free DFMA stream)",
