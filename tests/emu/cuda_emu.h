@@ -154,11 +154,18 @@ inline void a1emu_dmma884(double& d0, double& d1, double a, double b, double c0,
   ++a1emu::g_blk->n_mma;
   const int lane = a1emu::lane_id(), row = lane >> 2, col = 2 * (lane & 3);
   double r0 = c0, r1 = c1;
+  // arithmetic model of the tensor unit (PTX leaves the accumulation order open): 0 = chain of fused multiply-adds,
+  // 1 = products rounded, then added in k order, 2 = rounded products summed pairwise, then added to C
+  static const int model = std::getenv("A1EMU_DMMA_MODEL") ? std::atoi(std::getenv("A1EMU_DMMA_MODEL")) : 0;
+  double p0[4], p1[4];
   for (int k = 0; k < 4; ++k) {
     const double av = a1emu::u2d(w.slot[g & 1][row * 4 + k]);
-    r0 = std::fma(av, a1emu::u2d(w.slot2[g & 1][col * 4 + k]), r0);
-    r1 = std::fma(av, a1emu::u2d(w.slot2[g & 1][(col + 1) * 4 + k]), r1);
+    const double b0 = a1emu::u2d(w.slot2[g & 1][col * 4 + k]), b1 = a1emu::u2d(w.slot2[g & 1][(col + 1) * 4 + k]);
+    if (model == 0) { r0 = std::fma(av, b0, r0); r1 = std::fma(av, b1, r1); }
+    else { volatile double q0 = av * b0, q1 = av * b1; p0[k] = q0; p1[k] = q1; }
   }
+  if (model == 1) { for (int k = 0; k < 4; ++k) { r0 += p0[k]; r1 += p1[k]; } }
+  if (model == 2) { r0 += (p0[0] + p0[1]) + (p0[2] + p0[3]); r1 += (p1[0] + p1[1]) + (p1[2] + p1[3]); }
   // the operands of this collective stay valid until every lane has arrived at the NEXT one, so no second barrier
   d0 = r0;
   d1 = r1;

@@ -12,25 +12,23 @@ ROOT = os.path.dirname(os.path.dirname(_HERE))
 sys.path.insert(0, os.path.join(ROOT, "a1-qp-mpc-controller_b200"))
 import a1mpc  # noqa: E402  (struct definitions only; the emulator never touches liba1mpc.so)
 
-_LIB = None
+_LIBS = {}
 
 
-def lib(flags=""):
-    global _LIB
-    if _LIB is None:
-        env = dict(os.environ)
-        if flags:
-            env["EMUFLAGS"] = flags
-        subprocess.check_call(["make", "-C", _HERE, "-s"], env=env)
-        _LIB = C.CDLL(os.path.join(_HERE, "liba1mpc_emu.so"))
-    return _LIB
+def lib(variant=""):
+    """variant "" = the product's default switches; "hyst" = -DA1MPC_FIN_HYST=1"""
+    if variant not in _LIBS:
+        name = "liba1mpc_emu%s.so" % ("_" + variant if variant else "")
+        subprocess.check_call(["make", "-C", _HERE, "-s", name])
+        _LIBS[variant] = C.CDLL(os.path.join(_HERE, name))
+    return _LIBS[variant]
 
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def solve(cfg, st, sched=None, normals=None, order=0, nthreads=8, want_u=False):
+def solve(cfg, st, sched=None, normals=None, order=0, nthreads=8, want_u=False, variant=""):
     """st: dict x0[12,B] rot[9,B] foot[12,B] ref[9,B] contact[B]; returns f_body[12,B], status[B], iters[B] (, u_full), stats"""
     B = st["contact"].shape[0]
     arrs = [np.ascontiguousarray(st[k], dtype=np.float64) for k in ("x0", "rot", "foot", "ref")]
@@ -42,7 +40,7 @@ def solve(cfg, st, sched=None, normals=None, order=0, nthreads=8, want_u=False):
     sc = np.ascontiguousarray(sched, dtype=np.uint32) if sched is not None else None
     nm = np.ascontiguousarray(normals, dtype=np.float64) if normals is not None else None
     stats = (C.c_ulong * 2)()
-    rc = lib().emu_solve_batch(C.byref(cfg), B, C.byref(inp), _p(sc), _p(nm), C.byref(out), order, nthreads, stats)
+    rc = lib(variant).emu_solve_batch(C.byref(cfg), B, C.byref(inp), _p(sc), _p(nm), C.byref(out), order, nthreads, stats)
     assert rc == 0
     res = (f, status, iters) + ((u,) if want_u else ())
     return res + ({"collectives": int(stats[0]), "mma": int(stats[1])},)
