@@ -17,7 +17,7 @@ STATUS_OPTIMAL, STATUS_IPM_ONLY, STATUS_MAXITER, STATUS_NUMERICAL, STATUS_NO_CON
 
 EXPORTS = [
     "a1mpc_default_config", "a1mpc_create", "a1mpc_destroy", "a1mpc_last_error", "a1mpc_device_count",
-    "a1mpc_solve_batch", "a1mpc_solve_batch_ext", "a1mpc_build_qp_batch", "a1mpc_qp_mats_batch", "a1mpc_solve_dense_batch",
+    "a1mpc_solve_batch", "a1mpc_warm_bytes", "a1mpc_warm_reset", "a1mpc_solve_batch_warm", "a1mpc_solve_batch_ext", "a1mpc_build_qp_batch", "a1mpc_qp_mats_batch", "a1mpc_solve_dense_batch",
     "a1mpc_grf_qp_batch", "a1mpc_joint_torques_batch", "a1mpc_update_plan_batch", "a1mpc_device_alloc", "a1mpc_device_free", "a1mpc_host_alloc", "a1mpc_host_free",
     "a1mpc_memcpy_h2d", "a1mpc_memcpy_d2h", "a1mpc_sync", "a1mpc_event_create", "a1mpc_event_destroy",
     "a1mpc_event_record", "a1mpc_event_elapsed_ms", "a1mpc_launch_count", "a1mpc_measure_fp64_peak",
@@ -75,6 +75,7 @@ def lib():
         l = C.CDLL(LIB_PATH)
         l.a1mpc_last_error.restype = C.c_char_p
         l.a1mpc_launch_count.restype = C.c_int64
+        l.a1mpc_warm_bytes.restype = C.c_size_t
         l.a1mpc_launch_count.argtypes = [C.c_void_p]
         for name in ("a1mpc_device_alloc", "a1mpc_host_alloc"):
             getattr(l, name).argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
@@ -217,6 +218,23 @@ class Engine:
         out = Outputs(_p(f), _p(status), _p(iters), _p(u), B)
         _check(lib().a1mpc_solve_batch(self.h, B, C.byref(inp), C.byref(out)))
         return (f, status, iters, u) if want_u else (f, status, iters)
+
+    def warm_alloc(self, B):
+        """device-resident warm-start state for B robots (no guess yet); free with a1mpc_device_free / Engine.dfree"""
+        nbytes = lib().a1mpc_warm_bytes(self.h, B)
+        p = self.dalloc(nbytes)
+        _check(lib().a1mpc_warm_reset(self.h, p, B))
+        return p
+
+    def solve_warm(self, st, warm, shift=0):
+        """a1mpc_solve_batch_warm: host arrays in/out, `warm` from warm_alloc (updated in place on the device)"""
+        B = st["x0"].shape[1]
+        a = {k: np.ascontiguousarray(st[k], dtype=(np.uint32 if k == "contact" else np.float64)) for k in ("x0", "rot", "foot", "ref", "contact")}
+        f = np.zeros((12, B)); status = np.zeros(B, dtype=np.int32); iters = np.zeros(B, dtype=np.int32)
+        inp = Inputs(_p(a["x0"]), _p(a["rot"]), _p(a["foot"]), _p(a["ref"]), _p(a["contact"]), B)
+        out = Outputs(_p(f), _p(status), _p(iters), None, B)
+        _check(lib().a1mpc_solve_batch_warm(self.h, B, C.byref(inp), C.byref(out), warm, int(shift)))
+        return f, status, iters
 
     def solve_ext(self, st, sched=None, normals=None, want_u=False):
         """BASELINE config 4 (extension): per-step contact schedule [N,B] and/or terrain normals [12,B]"""

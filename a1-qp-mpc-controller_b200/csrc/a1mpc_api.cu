@@ -140,7 +140,7 @@ bool is_device_ptr(const void* p) {
 }
 
 // enqueue the fused path on device-resident SoA data
-int enqueue_solve(a1mpc_handle* h, int B, const DevInputs& din, const DevOutputs& dout) {
+int enqueue_solve(a1mpc_handle* h, int B, const DevInputs& din, const DevOutputs& dout, uint32_t* warm = nullptr, int shift = 0) {
   CK(cudaMemsetAsync(h->d_count, 0, 8 * sizeof(int), h->stream));
   pack_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(din, B, h->d_rec, (int)h->cap, h->d_count, dout, h->cfg.horizon);
   h->launches++;
@@ -155,6 +155,7 @@ int enqueue_solve(a1mpc_handle* h, int B, const DevInputs& din, const DevOutputs
     const bool prof = h->prof_on && h->prof_n < h->prof_cap;
     if (prof) CK(cudaEventRecord(h->prof_ev[((size_t)h->prof_n * 4 + (ns - 1)) * 2 + 0], st));
     if (!h->cls[ns].supported) unsupported_kernel<<<(B + 127) / 128, 128, 0, st>>>(rec, h->d_count, ns, dout, N);
+    else if (N == 10 && warm) fused_launch_n10_warm(ns, h->cls[ns], st, B, h->P, rec, h->d_count, dout, warm, shift);
     else if (N == 10) fused_launch_n10(ns, h->cls[ns], st, B, h->P, rec, h->d_count, dout);
     else fused_launch_n20(ns, h->cls[ns], st, B, h->P, rec, h->d_count, dout);
     h->launches++;
@@ -283,7 +284,7 @@ int a1mpc_destroy(a1mpc_handle* h) {
   return A1MPC_OK;
 }
 
-int a1mpc_solve_batch(a1mpc_handle* h, int B, const a1mpc_inputs* in, const a1mpc_outputs* out) {
+static int solve_batch_impl(a1mpc_handle* h, int B, const a1mpc_inputs* in, const a1mpc_outputs* out, uint32_t* warm, int shift) {
   if (!h || !in || !out) return fail(A1MPC_EINVAL, "null argument");
   if (B <= 0) return fail(A1MPC_EINVAL, "B must be positive");
   if (!in->x0 || !in->rot || !in->foot || !in->ref || !in->contact || !out->f_body || !out->status) return fail(A1MPC_EINVAL, "null input/output array");
@@ -297,7 +298,7 @@ int a1mpc_solve_batch(a1mpc_handle* h, int B, const a1mpc_inputs* in, const a1mp
     if ((rc = ensure_capacity(h, B, false, false))) return rc;
     DevInputs di{in->x0, in->rot, in->foot, in->ref, in->contact, in->ld};
     DevOutputs dout{out->f_body, out->status, out->iters, out->u_full, out->ld};
-    return enqueue_solve(h, B, di, dout);
+    return enqueue_solve(h, B, di, dout, warm, shift);
   }
   if ((rc = ensure_capacity(h, B, true, out->u_full != nullptr))) return rc;
   const size_t Bs = (size_t)B;
@@ -308,7 +309,7 @@ int a1mpc_solve_batch(a1mpc_handle* h, int B, const a1mpc_inputs* in, const a1mp
   CK(cudaMemcpyAsync(h->d_contact, in->contact, Bs * 4, cudaMemcpyHostToDevice, h->stream));
   DevInputs di{h->d_x0, h->d_rot, h->d_foot, h->d_ref, h->d_contact, Bs};
   DevOutputs dout{h->d_f, h->d_status, out->iters ? h->d_iters : nullptr, out->u_full ? h->d_u : nullptr, Bs};
-  if ((rc = enqueue_solve(h, B, di, dout))) return rc;
+  if ((rc = enqueue_solve(h, B, di, dout, warm, shift))) return rc;
   if ((rc = copy_rows(h->stream, out->f_body, out->ld, h->d_f, Bs, 12, Bs, 8, cudaMemcpyDeviceToHost))) return rc;
   CK(cudaMemcpyAsync(out->status, h->d_status, Bs * 4, cudaMemcpyDeviceToHost, h->stream));
   if (out->iters) CK(cudaMemcpyAsync(out->iters, h->d_iters, Bs * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -316,6 +317,30 @@ int a1mpc_solve_batch(a1mpc_handle* h, int B, const a1mpc_inputs* in, const a1mp
     if ((rc = copy_rows(h->stream, out->u_full, out->ld, h->d_u, Bs, 12 * h->cfg.horizon, Bs, 8, cudaMemcpyDeviceToHost))) return rc;
   CK(cudaStreamSynchronize(h->stream));
   return A1MPC_OK;
+}
+
+int a1mpc_solve_batch(a1mpc_handle* h, int B, const a1mpc_inputs* in, const a1mpc_outputs* out) { return solve_batch_impl(h, B, in, out, nullptr, 0); }
+
+size_t a1mpc_warm_bytes(const a1mpc_handle* h, int B) {
+  if (!h || B <= 0) return 0;
+  return (size_t)B * (size_t)(WARM_HDR + 4 * h->cfg.horizon) * sizeof(uint32_t);
+}
+
+int a1mpc_warm_reset(a1mpc_handle* h, void* warm, int B) {
+  if (!h || !warm || B <= 0) return fail(A1MPC_EINVAL, "null argument");
+  if (!is_device_ptr(warm)) return fail(A1MPC_EINVAL, "warm must be device memory (a1mpc_device_alloc)");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemsetAsync(warm, 0, a1mpc_warm_bytes(h, B), h->stream));
+  return A1MPC_OK;
+}
+
+int a1mpc_solve_batch_warm(a1mpc_handle* h, int B, const a1mpc_inputs* in, const a1mpc_outputs* out, void* warm, int shift) {
+  if (!h || !warm) return fail(A1MPC_EINVAL, "null argument");
+  if (h->cfg.horizon != 10) return fail(A1MPC_EINVAL, "warm start is implemented for horizon 10 (see include/a1mpc.h)");
+  if (shift < 0 || shift > h->cfg.horizon) return fail(A1MPC_EINVAL, "shift out of range");
+  CK(cudaSetDevice(h->device));
+  if (!is_device_ptr(warm)) return fail(A1MPC_EINVAL, "warm must be device memory (a1mpc_device_alloc)");
+  return solve_batch_impl(h, B, in, out, static_cast<uint32_t*>(warm), shift);
 }
 
 int a1mpc_solve_batch_ext(a1mpc_handle* h, int B, const a1mpc_inputs* in, const a1mpc_inputs_ext* ext, const a1mpc_outputs* out) {

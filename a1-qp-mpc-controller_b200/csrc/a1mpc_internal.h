@@ -17,6 +17,9 @@ cudaError_t fused_setup_n10(int sm_count, ClassLaunch (&cls)[5]);
 cudaError_t fused_setup_n20(int sm_count, ClassLaunch (&cls)[5]);
 void fused_launch_n10(int ns, const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count, const DevOutputs& out);
 void fused_launch_n20(int ns, const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count, const DevOutputs& out);
+// warm-started variant of the N = 10 classes (a1mpc_solve_batch_warm); set up by fused_setup_n10
+void fused_launch_n10_warm(int ns, const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count,
+                           const DevOutputs& out, uint32_t* warm, int shift);
 // extended path (per-step contact schedules + terrain normals), a1mpc_solve_ext.cu
 cudaError_t ext_setup(int horizon, int sm_count, ClassLaunch& c);
 void ext_launch(int horizon, const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count, const DevOutputs& out);

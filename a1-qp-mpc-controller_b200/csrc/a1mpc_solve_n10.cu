@@ -20,6 +20,20 @@ static cudaError_t setup_one(int sm_count, ClassLaunch& c) {
 }
 
 template <int NS, int N, int WPC, int LSM>
+static cudaError_t setup_one_warm(const ClassLaunch& c) {
+  return cudaFuncSetAttribute(solve_kernel_warm<NS, N, WPC, LSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+}
+
+template <int NS, int N, int WPC, int LSM>
+static void launch_one_warm(const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count,
+                            const DevOutputs& out, uint32_t* warm, int shift) {
+  int grid = (B + WPC - 1) / WPC;
+  if (grid > c.max_ctas) grid = c.max_ctas;
+  if (grid < 1) grid = 1;
+  solve_kernel_warm<NS, N, WPC, LSM><<<grid, 32 * WPC, c.smem, st>>>(P, rec, count, out, warm, shift);
+}
+
+template <int NS, int N, int WPC, int LSM>
 static void launch_one(const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count, const DevOutputs& out) {
   int grid = (B + WPC - 1) / WPC;
   if (grid > c.max_ctas) grid = c.max_ctas;
@@ -38,7 +52,18 @@ cudaError_t fused_setup_n10(int sm_count, ClassLaunch (&cls)[5]) {
   if ((e = setup_one<2, 10, A1MPC_WPC2, 0>(sm_count, cls[2])) != cudaSuccess) return e;
   if ((e = setup_one<3, 10, A1MPC_WPC34, 1>(sm_count, cls[3])) != cudaSuccess) return e;
   if ((e = setup_one<4, 10, A1MPC_WPC34, 1>(sm_count, cls[4])) != cudaSuccess) return e;
+  if ((e = setup_one_warm<1, 10, A1MPC_WPC1, 0>(cls[1])) != cudaSuccess) return e;
+  if ((e = setup_one_warm<2, 10, A1MPC_WPC2, 0>(cls[2])) != cudaSuccess) return e;
+  if ((e = setup_one_warm<3, 10, A1MPC_WPC34, 1>(cls[3])) != cudaSuccess) return e;
+  if ((e = setup_one_warm<4, 10, A1MPC_WPC34, 1>(cls[4])) != cudaSuccess) return e;
   return cudaSuccess;
+}
+void fused_launch_n10_warm(int ns, const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count,
+                           const DevOutputs& out, uint32_t* warm, int shift) {
+  if (ns == 1) launch_one_warm<1, 10, A1MPC_WPC1, 0>(c, st, B, P, rec, count, out, warm, shift);
+  if (ns == 2) launch_one_warm<2, 10, A1MPC_WPC2, 0>(c, st, B, P, rec, count, out, warm, shift);
+  if (ns == 3) launch_one_warm<3, 10, A1MPC_WPC34, 1>(c, st, B, P, rec, count, out, warm, shift);
+  if (ns == 4) launch_one_warm<4, 10, A1MPC_WPC34, 1>(c, st, B, P, rec, count, out, warm, shift);
 }
 void fused_launch_n10(int ns, const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count, const DevOutputs& out) {
   if (ns == 1) launch_one<1, 10, A1MPC_WPC1, 0>(c, st, B, P, rec, count, out);

@@ -119,6 +119,22 @@ int  a1mpc_device_count(void);
  * pointers: enqueued on the handle's stream, asynchronous (use a1mpc_sync). */
 int  a1mpc_solve_batch(a1mpc_handle* h, int B, const a1mpc_inputs* in, const a1mpc_outputs* out);
 
+/* ---- device-resident warm start across control ticks --------------------------------------------------
+ * The reference keeps ONE OsqpEigen::Solver alive and warm-starts every tick from the previous solution
+ * (A1RobotControl.h:67, A1RobotControl.cpp:522-538).  Here the state that is worth keeping is the optimal ACTIVE FACE of
+ * every robot: a1mpc_solve_batch_warm first runs the exact active-face finisher on the faces stored in `warm` by the
+ * previous call (a few reduced factorisations, no interior-point iteration when they still verify -- KKT-certified like
+ * every OPTIMAL result) and falls back to the cold path per robot otherwise; it then stores the new faces.  Results are
+ * the same optimum either way (the QP is strictly convex).
+ *   warm   DEVICE buffer of a1mpc_warm_bytes(h, B) bytes (a1mpc_device_alloc), owned by the caller, one slot per batch
+ *          index b; a1mpc_warm_reset (or zero bytes) = no guess.  A robot whose stance feet changed starts cold.
+ *   shift  how many horizon steps the stored faces move towards "now" (0: the problem is re-posed relative to the
+ *          current state every tick, as compute_grf does; 1: references fixed in absolute time).
+ * in / out as in a1mpc_solve_batch (host or device).  Horizon 10 only in this round (A1MPC_EINVAL otherwise). */
+size_t a1mpc_warm_bytes(const a1mpc_handle* h, int B);
+int  a1mpc_warm_reset(a1mpc_handle* h, void* warm, int B);
+int  a1mpc_solve_batch_warm(a1mpc_handle* h, int B, const a1mpc_inputs* in, const a1mpc_outputs* out, void* warm, int shift);
+
 /* ---- BASELINE config 4: an EXTENSION beyond the reference (which keeps one contact pattern over the horizon,
  * ConvexMpc.cpp:226-245, and world-z friction pyramids) ------------------------------------------------ */
 /*   contact_sched [N][B]  contact mask of every horizon step (batch-major, ld of `in`), or NULL = in->contact everywhere

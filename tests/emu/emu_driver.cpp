@@ -30,7 +30,8 @@ DevParams make_params(const a1mpc_config* cfg) {   // a1mpc_create() in a1mpc_ap
 struct Stats { std::atomic<unsigned long> collectives{0}, mma{0}; };
 
 template <int NS, int N, int WPC, int LSM, bool EXT>
-void run_class(const DevParams& P, const double* rec, const int* count, const DevOutputs& out, int order_mode, int nthreads, Stats& st) {
+void run_class(const DevParams& P, const double* rec, const int* count, const DevOutputs& out, int order_mode, int nthreads, Stats& st,
+               uint32_t* warm = nullptr, int shift = 0) {
   using G = Geo<NS, N, LSM>;
   const int nq = count[EXT ? 5 : NS];
   if (nq == 0) return;
@@ -42,7 +43,12 @@ void run_class(const DevParams& P, const double* rec, const int* count, const De
       if (bx >= grid) break;
       unsigned long nc = 0, nm = 0;
       a1emu::run_block(a1emu::Dim3{(unsigned)bx, 0, 0}, a1emu::Dim3{(unsigned)grid, 1, 1}, 32 * WPC, G::smem_bytes(WPC), order_mode,
-                       [&]() { solve_kernel<NS, N, WPC, LSM, EXT>(P, rec, count, out); }, &nc, &nm);
+                       [&]() {
+                         if constexpr (!EXT) {
+                           if (warm) { solve_kernel_warm<NS, N, WPC, LSM>(P, rec, count, out, warm, shift); return; }
+                         }
+                         solve_kernel<NS, N, WPC, LSM, EXT>(P, rec, count, out);
+                       }, &nc, &nm);
       st.collectives += nc;
       st.mma += nm;
     }
@@ -54,16 +60,19 @@ void run_class(const DevParams& P, const double* rec, const int* count, const De
 }
 
 template <int N>
-void run_all(const DevParams& P, const double* rec, size_t cap, const int* count, const DevOutputs& out, int order_mode, int nthreads, Stats& st);
+void run_all(const DevParams& P, const double* rec, size_t cap, const int* count, const DevOutputs& out, int order_mode, int nthreads, Stats& st,
+             uint32_t* warm, int shift);
 template <>
-void run_all<10>(const DevParams& P, const double* rec, size_t cap, const int* count, const DevOutputs& out, int order_mode, int nthreads, Stats& st) {
-  run_class<1, 10, A1MPC_WPC1, 0, false>(P, rec + 0 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st);
-  run_class<2, 10, A1MPC_WPC2, 0, false>(P, rec + 1 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st);
-  run_class<3, 10, A1MPC_WPC34, 1, false>(P, rec + 2 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st);
-  run_class<4, 10, A1MPC_WPC34, 1, false>(P, rec + 3 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st);
+void run_all<10>(const DevParams& P, const double* rec, size_t cap, const int* count, const DevOutputs& out, int order_mode, int nthreads, Stats& st,
+                 uint32_t* warm, int shift) {
+  run_class<1, 10, A1MPC_WPC1, 0, false>(P, rec + 0 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st, warm, shift);
+  run_class<2, 10, A1MPC_WPC2, 0, false>(P, rec + 1 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st, warm, shift);
+  run_class<3, 10, A1MPC_WPC34, 1, false>(P, rec + 2 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st, warm, shift);
+  run_class<4, 10, A1MPC_WPC34, 1, false>(P, rec + 3 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st, warm, shift);
 }
 template <>
-void run_all<20>(const DevParams& P, const double* rec, size_t cap, const int* count, const DevOutputs& out, int order_mode, int nthreads, Stats& st) {
+void run_all<20>(const DevParams& P, const double* rec, size_t cap, const int* count, const DevOutputs& out, int order_mode, int nthreads, Stats& st,
+                 uint32_t*, int) {
   run_class<1, 20, 2, 0, false>(P, rec + 0 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st);
   run_class<2, 20, 1, 0, false>(P, rec + 1 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st);
   run_class<3, 20, 1, 1, false>(P, rec + 2 * cap * REC_DOUBLES, count, out, order_mode, nthreads, st);
@@ -132,8 +141,9 @@ int emu_grf_qp(int B, const double* root_acc, const double* rot_z, const double*
 
 // Same contract as a1mpc_solve_batch / a1mpc_solve_batch_ext with host pointers.  order_mode: lane order between
 // collectives (0 ascending, 1 descending, 2 pseudo-random).  stats[0] = warp collectives executed, stats[1] = DMMAs.
+// warm: host buffer of B * (4 + 4 * horizon) u32 (zero = no guess), N = 10 only -- the emulated a1mpc_solve_batch_warm
 int emu_solve_batch(const a1mpc_config* cfg, int B, const a1mpc_inputs* in, const uint32_t* sched, const double* normals,
-                    const a1mpc_outputs* o, int order_mode, int nthreads, unsigned long* stats) {
+                    const a1mpc_outputs* o, int order_mode, int nthreads, unsigned long* stats, uint32_t* warm, int shift) {
   if (cfg->horizon != 10 && cfg->horizon != 20) return -1;
   const DevParams P = make_params(cfg);
   const DevInputs din{in->x0, in->rot, in->foot, in->ref, in->contact, in->ld};
@@ -154,8 +164,9 @@ int emu_solve_batch(const a1mpc_config* cfg, int B, const a1mpc_inputs* in, cons
   }
   if (nthreads < 1) nthreads = 1;
   if (!ext) {
-    if (cfg->horizon == 10) run_all<10>(P, rec.data(), cap, count, dout, order_mode, nthreads, st);
-    else run_all<20>(P, rec.data(), cap, count, dout, order_mode, nthreads, st);
+    if (warm && cfg->horizon != 10) return -2;
+    if (cfg->horizon == 10) run_all<10>(P, rec.data(), cap, count, dout, order_mode, nthreads, st, warm, shift);
+    else run_all<20>(P, rec.data(), cap, count, dout, order_mode, nthreads, st, nullptr, 0);
   } else {
     if (cfg->horizon == 10) run_class<4, 10, 1, 1, true>(P, rec.data(), count, dout, order_mode, nthreads, st);
     else run_class<4, 20, 1, 1, true>(P, rec.data(), count, dout, order_mode, nthreads, st);

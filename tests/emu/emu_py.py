@@ -28,7 +28,7 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def solve(cfg, st, sched=None, normals=None, order=0, nthreads=8, want_u=False, variant=""):
+def solve(cfg, st, sched=None, normals=None, order=0, nthreads=8, want_u=False, variant="", warm=None, shift=1):
     """st: dict x0[12,B] rot[9,B] foot[12,B] ref[9,B] contact[B]; returns f_body[12,B], status[B], iters[B] (, u_full), stats"""
     B = st["contact"].shape[0]
     arrs = [np.ascontiguousarray(st[k], dtype=np.float64) for k in ("x0", "rot", "foot", "ref")]
@@ -40,7 +40,9 @@ def solve(cfg, st, sched=None, normals=None, order=0, nthreads=8, want_u=False, 
     sc = np.ascontiguousarray(sched, dtype=np.uint32) if sched is not None else None
     nm = np.ascontiguousarray(normals, dtype=np.float64) if normals is not None else None
     stats = (C.c_ulong * 2)()
-    rc = lib(variant).emu_solve_batch(C.byref(cfg), B, C.byref(inp), _p(sc), _p(nm), C.byref(out), order, nthreads, stats)
+    if warm is not None:
+        assert warm.dtype == np.uint32 and warm.shape == (B, 4 + 4 * cfg.horizon) and warm.flags["C_CONTIGUOUS"]
+    rc = lib(variant).emu_solve_batch(C.byref(cfg), B, C.byref(inp), _p(sc), _p(nm), C.byref(out), order, nthreads, stats, _p(warm), shift)
     assert rc == 0
     res = (f, status, iters) + ((u,) if want_u else ())
     return res + ({"collectives": int(stats[0]), "mma": int(stats[1])},)

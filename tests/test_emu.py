@@ -146,3 +146,38 @@ def test_degenerate_vertex_family_is_explicit_and_fixed_by_hysteresis(E, a1, O):
     assert np.abs(f - fo)[:, status == a1.STATUS_OPTIMAL].max() < 1e-7
     f2, status2, iters2, _ = E.solve(cfg, st, variant="hyst")
     assert (status2 == a1.STATUS_OPTIMAL).all() and np.abs(f2 - fo).max() < 1e-7 and (iters2 // 100).max() <= 6
+
+
+def test_warm_start_across_ticks_on_emulator(E, a1, O):
+    """the device-resident warm start (a1mpc_solve_batch_warm) -- the previous tick's verified active faces are the
+    first guess of the finisher; a hit costs 1-2 reduced factorisations and no interior-point iteration, a miss falls back to
+    the cold path; the optimum is the same either way."""
+    B = 160
+    cfg = a1.default_config(horizon=10)
+    st = a1.gen_states(B, 2, 5)
+    for i, p in enumerate([1, 2, 4, 8, 7, 11, 13, 14, 15, 0]):
+        st["contact"][i] = p
+    warm = np.zeros((B, 4 + 4 * 10), dtype=np.uint32)
+    f1, s1, it1, _ = E.solve(cfg, st, warm=warm, shift=0)
+    nz = st["contact"] != 0
+    assert (s1[nz] == a1.STATUS_OPTIMAL).all() and (warm[nz, 0] == 1).all() and (warm[~nz, 0] == 0).all()
+    assert ((it1 % 100)[nz] > 0).all()                       # no guess yet: every robot took the interior-point path
+    fo1, _ = O.compute_grf_batch(O.make_config(horizon=10), obatch(O, st), mode=O.MODE_EXACT, nthreads=4)
+    assert np.abs(f1 - fo1).max() <= TOL_F
+    # next tick: the state advances by dt plus sensor-level noise; a few robots change their stance set
+    rng = np.random.default_rng(0)
+    st2 = {k: v.copy() for k, v in st.items()}
+    st2["x0"][3:6] += 0.0025 * st["x0"][9:12]
+    st2["x0"][0:3] += 0.0025 * st["x0"][6:9]
+    st2["x0"] += 0.03 * rng.standard_normal(st2["x0"].shape) * np.array([.02, .02, .02, .01, .01, .005, .1, .1, .1, .05, .05, .05])[:, None]
+    st2["contact"][20:24] = [3, 5, 15, 6]
+    changed = st2["contact"] != st["contact"]
+    f2, s2, it2, _ = E.solve(cfg, st2, warm=warm, shift=0, order=2)
+    fo2, _ = O.compute_grf_batch(O.make_config(horizon=10), obatch(O, st2), mode=O.MODE_EXACT, nthreads=4)
+    assert (s2[nz] == a1.STATUS_OPTIMAL).all() and np.abs(f2 - fo2).max() <= TOL_F and np.abs(f2 - fo2).max() < 1e-7
+    hit = ((it2 % 100) == 0) & nz
+    assert not hit[changed].any()                            # different stance feet: cold start
+    assert hit[nz & ~changed].mean() > 0.8                   # most robots keep their active faces from one tick to the next
+    fact_warm = (it2 % 100 + it2 // 100)[nz & ~changed].mean()
+    fact_cold = (it1 % 100 + it1 // 100)[nz].mean()
+    assert fact_warm < 0.5 * fact_cold, (fact_warm, fact_cold)
