@@ -18,7 +18,7 @@ STATUS_OPTIMAL, STATUS_IPM_ONLY, STATUS_MAXITER, STATUS_NUMERICAL, STATUS_NO_CON
 EXPORTS = [
     "a1mpc_default_config", "a1mpc_create", "a1mpc_destroy", "a1mpc_last_error", "a1mpc_device_count",
     "a1mpc_solve_batch", "a1mpc_warm_bytes", "a1mpc_warm_reset", "a1mpc_solve_batch_warm", "a1mpc_solve_batch_ext", "a1mpc_build_qp_batch", "a1mpc_qp_mats_batch", "a1mpc_solve_dense_batch",
-    "a1mpc_grf_qp_batch", "a1mpc_joint_torques_batch", "a1mpc_update_plan_batch", "a1mpc_device_alloc", "a1mpc_device_free", "a1mpc_host_alloc", "a1mpc_host_free",
+    "a1mpc_grf_qp_batch", "a1mpc_joint_torques_batch", "a1mpc_leg_kinematics_batch", "a1mpc_ekf_bytes", "a1mpc_ekf_init_batch", "a1mpc_ekf_update_batch", "a1mpc_update_plan_batch", "a1mpc_device_alloc", "a1mpc_device_free", "a1mpc_host_alloc", "a1mpc_host_free",
     "a1mpc_memcpy_h2d", "a1mpc_memcpy_d2h", "a1mpc_sync", "a1mpc_event_create", "a1mpc_event_destroy",
     "a1mpc_event_record", "a1mpc_event_elapsed_ms", "a1mpc_launch_count", "a1mpc_measure_fp64_peak",
     "a1mpc_flush_l2", "a1mpc_profile_begin", "a1mpc_profile_end", "a1mpc_nccl_unique_id", "a1mpc_nccl_init", "a1mpc_allgather_forces", "a1mpc_gen_states", "a1mpc_gen_schedule",
@@ -76,6 +76,7 @@ def lib():
         l.a1mpc_last_error.restype = C.c_char_p
         l.a1mpc_launch_count.restype = C.c_int64
         l.a1mpc_warm_bytes.restype = C.c_size_t
+        l.a1mpc_ekf_bytes.restype = C.c_size_t
         l.a1mpc_launch_count.argtypes = [C.c_void_p]
         for name in ("a1mpc_device_alloc", "a1mpc_host_alloc"):
             getattr(l, name).argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
@@ -299,6 +300,40 @@ class Engine:
         tau = np.zeros((12, B)) if tau_prev is None else np.ascontiguousarray(tau_prev, dtype=np.float64).copy()
         _check(lib().a1mpc_joint_torques_batch(self.h, B, _p(a[0]), _p(a[1]), _p(a[2]), _p(contact), _p(a[3]), _p(a[4]), _p(tau)))
         return tau
+
+    def leg_kinematics(self, joint_pos, joint_vel, rot, rho_opt, rho_fix):
+        """a1mpc_leg_kinematics_batch, host arrays: [12,B], [12,B], [9,B], rho_opt[12], rho_fix[20] ->
+        foot_pos_rel [12,B], jac [36,B], foot_vel_rel [12,B], foot_pos_abs [12,B], foot_vel_abs [12,B]"""
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (joint_pos, joint_vel, rot, rho_opt, rho_fix)]
+        B = a[0].shape[1]
+        outs = [np.zeros((12, B)), np.zeros((36, B)), np.zeros((12, B)), np.zeros((12, B)), np.zeros((12, B))]
+        _check(lib().a1mpc_leg_kinematics_batch(self.h, B, *[_p(v) for v in a], *[_p(o) for o in outs]))
+        return outs
+
+    def ekf_alloc(self, B):
+        """device-resident filter state of B robots (342 doubles each: x[18], P[18,18])"""
+        return self.dalloc(lib().a1mpc_ekf_bytes(B))
+
+    def ekf_init(self, ekf, foot_pos_rel, rot):
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (foot_pos_rel, rot)]
+        _check(lib().a1mpc_ekf_init_batch(self.h, a[0].shape[1], ekf, _p(a[0]), _p(a[1])))
+
+    def ekf_update(self, ekf, dt, assume_flat_ground, movement_mode, imu_acc, imu_ang_vel, rot, foot_pos_rel, foot_vel_rel, foot_force):
+        """a1mpc_ekf_update_batch, host arrays -> root_pos [3,B], root_lin_vel [3,B], estimated_contacts [B], status [B]"""
+        mm = np.ascontiguousarray(movement_mode, dtype=np.uint32)
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (imu_acc, imu_ang_vel, rot, foot_pos_rel, foot_vel_rel, foot_force)]
+        B = mm.shape[0]
+        pos = np.zeros((3, B)); vel = np.zeros((3, B)); ec = np.zeros(B, dtype=np.uint32); status = np.full(B, -7, dtype=np.int32)
+        _check(lib().a1mpc_ekf_update_batch(self.h, B, ekf, C.c_double(dt), int(assume_flat_ground), _p(mm), *[_p(v) for v in a],
+                                            _p(pos), _p(vel), _p(ec), _p(status)))
+        return pos, vel, ec, status
+
+    def ekf_state(self, ekf, B):
+        """copy of the device-resident filter state: x [B,18], P [B,18,18]"""
+        buf = np.zeros((B, 342))
+        _check(lib().a1mpc_memcpy_d2h(self.h, _p(buf), ekf, buf.nbytes))
+        _check(lib().a1mpc_sync(self.h))
+        return buf[:, :18].copy(), buf[:, 18:].reshape(B, 18, 18).copy()
 
     def update_plan(self, gp, gait_counter, gait_counter_speed, movement_mode, lin_vel, lin_vel_d, rot_z, rot, root_pos):
         """A1RobotControl::update_plan batched; returns new gait_counter [4,B], plan_contacts [B], contact_sched [N,B],

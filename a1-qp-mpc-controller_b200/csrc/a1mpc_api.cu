@@ -10,6 +10,7 @@
 
 #include "a1mpc_internal.h"
 #include "a1mpc_misc.cuh"
+#include "a1mpc_estim.cuh"
 
 using namespace a1mpc;
 
@@ -669,6 +670,134 @@ int a1mpc_update_plan_batch(a1mpc_handle* h, int B, const a1mpc_gait_params* gp,
   if (t_world) CK(cudaMemcpyAsync(t_world, d_tw, 12 * Bs * 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return A1MPC_OK;
+}
+
+// ---- upstream producers of the path's inputs ---------------------------------------------------
+}  // extern "C"
+namespace {
+// host-pointer mode of the side entry points: inputs are staged into h->d_side, outputs copied back after the kernel
+struct Stage {
+  a1mpc_handle* h;
+  bool host;
+  char* cur = nullptr;
+  struct Out { void* host; const void* dev; size_t bytes; };
+  std::vector<Out> outs;
+  static size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
+  template <class T>
+  int in(const T*& p, size_t bytes) {
+    if (!host || !p) return A1MPC_OK;
+    CK(cudaMemcpyAsync(cur, p, bytes, cudaMemcpyHostToDevice, h->stream));
+    p = reinterpret_cast<const T*>(cur);
+    cur += pad(bytes);
+    return A1MPC_OK;
+  }
+  template <class T>
+  void out(T*& p, size_t bytes) {
+    if (!host || !p) return;
+    outs.push_back({p, cur, bytes});
+    p = reinterpret_cast<T*>(cur);
+    cur += pad(bytes);
+  }
+  int finish() {
+    if (!host) return A1MPC_OK;
+    for (const Out& o : outs) CK(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return A1MPC_OK;
+  }
+};
+}  // namespace
+extern "C" {
+
+int a1mpc_leg_kinematics_batch(a1mpc_handle* h, int B, const double* joint_pos, const double* joint_vel, const double* rot,
+                               const double* rho_opt, const double* rho_fix, double* foot_pos_rel, double* jac, double* foot_vel_rel,
+                               double* foot_pos_abs, double* foot_vel_abs) {
+  if (!h || !joint_pos || !rho_opt || !rho_fix) return fail(A1MPC_EINVAL, "null argument");
+  if (B <= 0) return fail(A1MPC_EINVAL, "B must be positive");
+  if ((foot_vel_rel || foot_vel_abs) && !joint_vel) return fail(A1MPC_EINVAL, "foot velocities need joint_vel");
+  if ((foot_pos_abs || foot_vel_abs) && !rot) return fail(A1MPC_EINVAL, "body-aligned outputs need rot");
+  CK(cudaSetDevice(h->device));
+  const size_t Bs = (size_t)B;
+  LegParams P;
+  for (int i = 0; i < 12; ++i) P.rho_opt[i] = rho_opt[i];
+  for (int i = 0; i < 20; ++i) P.rho_fix[i] = rho_fix[i];
+  Stage st{h, !is_device_ptr(joint_pos)};
+  int rc;
+  if (st.host) {
+    if ((rc = ensure_side(h, 8 * Stage::pad(36 * Bs * 8)))) return rc;
+    st.cur = (char*)h->d_side;
+  }
+  if ((rc = st.in(joint_pos, 12 * Bs * 8))) return rc;
+  if ((rc = st.in(joint_vel, 12 * Bs * 8))) return rc;
+  if ((rc = st.in(rot, 9 * Bs * 8))) return rc;
+  st.out(foot_pos_rel, 12 * Bs * 8); st.out(jac, 36 * Bs * 8); st.out(foot_vel_rel, 12 * Bs * 8);
+  st.out(foot_pos_abs, 12 * Bs * 8); st.out(foot_vel_abs, 12 * Bs * 8);
+  leg_kinematics_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(B, joint_pos, joint_vel, rot, P, foot_pos_rel, jac, foot_vel_rel, foot_pos_abs, foot_vel_abs);
+  h->launches++;
+  CK(cudaGetLastError());
+  return st.finish();
+}
+
+size_t a1mpc_ekf_bytes(int B) { return B > 0 ? (size_t)B * EKF_STATE_DOUBLES * sizeof(double) : 0; }
+
+int a1mpc_ekf_init_batch(a1mpc_handle* h, int B, void* ekf_state, const double* foot_pos_rel, const double* rot) {
+  if (!h || !ekf_state || !foot_pos_rel || !rot) return fail(A1MPC_EINVAL, "null argument");
+  if (B <= 0) return fail(A1MPC_EINVAL, "B must be positive");
+  CK(cudaSetDevice(h->device));
+  if (!is_device_ptr(ekf_state)) return fail(A1MPC_EINVAL, "ekf_state must be device memory (a1mpc_device_alloc)");
+  const size_t Bs = (size_t)B;
+  Stage st{h, !is_device_ptr(foot_pos_rel)};
+  int rc;
+  if (st.host) {
+    if ((rc = ensure_side(h, 2 * Stage::pad(12 * Bs * 8)))) return rc;
+    st.cur = (char*)h->d_side;
+  }
+  if ((rc = st.in(foot_pos_rel, 12 * Bs * 8))) return rc;
+  if ((rc = st.in(rot, 9 * Bs * 8))) return rc;
+  ekf_init_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(B, static_cast<double*>(ekf_state), foot_pos_rel, rot);
+  h->launches++;
+  CK(cudaGetLastError());
+  return st.finish();
+}
+
+int a1mpc_ekf_update_batch(a1mpc_handle* h, int B, void* ekf_state, double dt, int assume_flat_ground, const uint32_t* movement_mode,
+                           const double* imu_acc, const double* imu_ang_vel, const double* rot, const double* foot_pos_rel,
+                           const double* foot_vel_rel, const double* foot_force, double* root_pos, double* root_lin_vel,
+                           uint32_t* estimated_contacts, int32_t* status) {
+  if (!h || !ekf_state || !movement_mode || !imu_acc || !imu_ang_vel || !rot || !foot_pos_rel || !foot_vel_rel || !foot_force)
+    return fail(A1MPC_EINVAL, "null argument");
+  if (B <= 0) return fail(A1MPC_EINVAL, "B must be positive");
+  if (!(dt > 0.0)) return fail(A1MPC_EINVAL, "dt must be positive");
+  CK(cudaSetDevice(h->device));
+  if (!is_device_ptr(ekf_state)) return fail(A1MPC_EINVAL, "ekf_state must be device memory (a1mpc_device_alloc)");
+  static bool attr_set[64] = {};
+  const size_t smem = (size_t)EKF_WPC * EKF_WARP_DOUBLES * sizeof(double);
+  if (h->device < 64 && !attr_set[h->device]) {
+    CK(cudaFuncSetAttribute(ekf_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[h->device] = true;
+  }
+  const size_t Bs = (size_t)B;
+  Stage st{h, !is_device_ptr(imu_acc)};
+  int rc;
+  if (st.host) {
+    if ((rc = ensure_side(h, 12 * Stage::pad(12 * Bs * 8)))) return rc;
+    st.cur = (char*)h->d_side;
+  }
+  if ((rc = st.in(movement_mode, Bs * 4))) return rc;
+  if ((rc = st.in(imu_acc, 3 * Bs * 8))) return rc;
+  if ((rc = st.in(imu_ang_vel, 3 * Bs * 8))) return rc;
+  if ((rc = st.in(rot, 9 * Bs * 8))) return rc;
+  if ((rc = st.in(foot_pos_rel, 12 * Bs * 8))) return rc;
+  if ((rc = st.in(foot_vel_rel, 12 * Bs * 8))) return rc;
+  if ((rc = st.in(foot_force, 4 * Bs * 8))) return rc;
+  st.out(root_pos, 3 * Bs * 8); st.out(root_lin_vel, 3 * Bs * 8); st.out(estimated_contacts, Bs * 4); st.out(status, Bs * 4);
+  EkfParams P{dt, assume_flat_ground ? 1 : 0};
+  int grid = (B + EKF_WPC - 1) / EKF_WPC;
+  if (grid > h->sm_count * 2) grid = h->sm_count * 2;
+  ekf_update_kernel<<<grid, 32 * EKF_WPC, smem, h->stream>>>(B, P, static_cast<double*>(ekf_state), movement_mode, imu_acc, imu_ang_vel, rot,
+                                                             foot_pos_rel, foot_vel_rel, foot_force, root_pos, root_lin_vel, estimated_contacts, status);
+  h->launches++;
+  CK(cudaGetLastError());
+  return st.finish();
 }
 
 // ---- helpers -------------------------------------------------------------------------------

@@ -192,6 +192,38 @@ int  a1mpc_grf_qp_batch(a1mpc_handle* h, int B, const double* root_acc, const do
 int  a1mpc_joint_torques_batch(a1mpc_handle* h, int B, const double* f_grf, const double* f_kin, const double* jac,
                                const uint32_t* contact, const double* km_foot, const double* torques_gravity, double* tau);
 
+/* ---- upstream producers of the path's inputs ------------------------------------------------------ */
+/* Leg forward kinematics and Jacobian: A1Kinematics::fk / jac (legKinematics/A1Kinematics.cpp:7-18; bodies :39-131) with the
+ * per-tick derived quantities of GazeboA1ROS.cpp:264-279, batched.  Batch-major SoA (ld = B), host or device pointers:
+ *   joint_pos [12][B] leg-major (FL, FR, RL, RR) x (hip, thigh, calf); joint_vel [12][B] (NULL: no velocities)
+ *   rot [9][B] root_rot_mat row-major (NULL: no *_abs outputs)
+ *   rho_opt [12] = 4 legs x (cx, cy, cz) contact offset; rho_fix [20] = 4 legs x (leg_offset_x, leg_offset_y, motor_offset,
+ *   upper_leg_length, lower_leg_length) (GazeboA1ROS.cpp:76-97): HOST arrays, batch-uniform
+ *   out (any may be NULL): foot_pos_rel [12][B]; jac [36][B] = the four 3x3 blocks of j_foot, leg-major then row-major (the
+ *   layout a1mpc_joint_torques_batch takes); foot_vel_rel [12][B] = J dq; foot_pos_abs [12][B] = R foot_pos_rel (the `foot`
+ *   input of a1mpc_solve_batch); foot_vel_abs [12][B]. */
+int  a1mpc_leg_kinematics_batch(a1mpc_handle* h, int B, const double* joint_pos, const double* joint_vel, const double* rot,
+                                const double* rho_opt, const double* rho_fix, double* foot_pos_rel, double* jac, double* foot_vel_rel,
+                                double* foot_pos_abs, double* foot_vel_abs);
+
+/* A1BasicEKF (A1BasicEKF.cpp), batched: 18 states (position, velocity, four foot positions), 28 measurements, orientation
+ * taken from the IMU.  The filter state lives on the device: a1mpc_ekf_bytes(B) bytes (a1mpc_device_alloc), per robot 342
+ * doubles = x[18], P[18][18] row-major.
+ *   a1mpc_ekf_init_batch    A1BasicEKF::init_state (:56-68): P = 3 I, x = (0, 0, 0.09, 0, 0, 0, R fk_i + pos)
+ *   a1mpc_ekf_update_batch  A1BasicEKF::update_estimation (:70-164) with the constructor's C, Q, R (:7-53; noise constants of
+ *                           A1BasicEKF.h:16-21): contact estimate from movement_mode / foot_force, process update, measurement,
+ *                           S = C Pbar C' + R, x and P update, position-drift cut (:144-148)
+ *   batch-major SoA inputs (ld = B), host or device: movement_mode [B], imu_acc [3][B], imu_ang_vel [3][B], rot [9][B],
+ *   foot_pos_rel [12][B], foot_vel_rel [12][B], foot_force [4][B]
+ *   out (any may be NULL): root_pos [3][B] (= estimated_root_pos), root_lin_vel [3][B], estimated_contacts [B] (bit i = leg i),
+ *   status [B]: 0, or A1MPC_STATUS_NUMERICAL when S is not positive definite / not finite (that robot's state is untouched). */
+size_t a1mpc_ekf_bytes(int B);
+int  a1mpc_ekf_init_batch(a1mpc_handle* h, int B, void* ekf_state, const double* foot_pos_rel, const double* rot);
+int  a1mpc_ekf_update_batch(a1mpc_handle* h, int B, void* ekf_state, double dt, int assume_flat_ground, const uint32_t* movement_mode,
+                            const double* imu_acc, const double* imu_ang_vel, const double* rot, const double* foot_pos_rel,
+                            const double* foot_vel_rel, const double* foot_force, double* root_pos, double* root_lin_vel,
+                            uint32_t* estimated_contacts, int32_t* status);
+
 /* ---- the step right before the path: A1RobotControl::update_plan ------------------------ */
 /* Gait counters -> planned contacts, and the Raibert foothold targets (A1RobotControl.cpp:148-202), batched; plus what the
  * reference does not do: the planned contact mask of every horizon step (it freezes the current pattern,

@@ -1379,6 +1379,168 @@ int oracle_update_plan(double counter_per_gait, double counter_per_swing, double
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Leg kinematics.  A1Kinematics::fk / jac (legKinematics/A1Kinematics.cpp:7-18) evaluate Matlab-generated
+// expansions (:39-131) of the A1 leg chain.  Restated here AS THE CHAIN ITSELF -- hip at (ox, oy, 0), roll q0 about x, thigh
+// offset d along y, pitch q1 about y, upper link lt down, pitch q2 about y, lower link lc down, contact offset (cx,cy,cz) --
+// with the geometric Jacobian (axis x lever arm), i.e. independently of the closed form the CUDA kernel uses.
+// PINNED: oracle/_ref (built in the authoring container from the reference's own A1Kinematics.cpp against a stub of the
+// two Eigen types it touches) agrees with this function to 1e-15, and tests/golden/kinematics_v1.json holds vectors
+// generated from that build.
+// p[3], J[9] row-major (J[3*a + k] = d p_a / d q_k).
+// ---------------------------------------------------------------------------------------------------------------------
+static void rot_x(double t, double (&R)[3][3]) { const double c = std::cos(t), s = std::sin(t); double M[3][3] = {{1, 0, 0}, {0, c, -s}, {0, s, c}}; std::memcpy(R, M, sizeof(M)); }
+static void rot_y(double t, double (&R)[3][3]) { const double c = std::cos(t), s = std::sin(t); double M[3][3] = {{c, 0, s}, {0, 1, 0}, {-s, 0, c}}; std::memcpy(R, M, sizeof(M)); }
+static void mat_vec3(const double (&R)[3][3], const double* v, double* o) { for (int a = 0; a < 3; ++a) o[a] = R[a][0] * v[0] + R[a][1] * v[1] + R[a][2] * v[2]; }
+static void mat_mat3(const double (&A)[3][3], const double (&B)[3][3], double (&C)[3][3]) {
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) C[i][j] = A[i][0] * B[0][j] + A[i][1] * B[1][j] + A[i][2] * B[2][j];
+}
+static void cross3(const double* a, const double* b, double* o) { o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0]; }
+
+int oracle_leg_kinematics(const double* q, const double* rho_opt, const double* rho_fix, double* p, double* J) {
+  const double ox = rho_fix[0], oy = rho_fix[1], d = rho_fix[2], lt = rho_fix[3], lc = rho_fix[4];
+  double Rx[3][3], Ry1[3][3], Ry2[3][3], R01[3][3], R012[3][3];
+  rot_x(q[0], Rx); rot_y(q[1], Ry1); rot_y(q[2], Ry2);
+  mat_mat3(Rx, Ry1, R01); mat_mat3(R01, Ry2, R012);
+  const double hip[3] = {ox, oy, 0.0};
+  const double off_thigh[3] = {0.0, d, 0.0}, link_up[3] = {0.0, 0.0, -lt}, tip[3] = {rho_opt[0], rho_opt[1], rho_opt[2] - lc};
+  double t0[3], t1[3], t2[3];
+  mat_vec3(Rx, off_thigh, t0); mat_vec3(R01, link_up, t1); mat_vec3(R012, tip, t2);
+  double o1[3], o2[3];
+  for (int a = 0; a < 3; ++a) { o1[a] = hip[a] + t0[a]; o2[a] = o1[a] + t1[a]; p[a] = o2[a] + t2[a]; }
+  const double ex[3] = {1, 0, 0}, ey[3] = {0, 1, 0};
+  double ax1[3];
+  mat_vec3(Rx, ey, ax1);               // both pitch joints turn about the rolled y axis
+  double l0[3], l1[3], l2[3], c0[3], c1[3], c2[3];
+  for (int a = 0; a < 3; ++a) { l0[a] = p[a] - hip[a]; l1[a] = p[a] - o1[a]; l2[a] = p[a] - o2[a]; }
+  cross3(ex, l0, c0); cross3(ax1, l1, c1); cross3(ax1, l2, c2);
+  for (int a = 0; a < 3; ++a) { J[3 * a] = c0[a]; J[3 * a + 1] = c1[a]; J[3 * a + 2] = c2[a]; }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// A1BasicEKF, literal restatement with the dense matrices of the reference: constructor :7-41 (C, Q, R, A, B),
+// init_state :56-68, update_estimation :70-164.  x[18], P[18*18] row-major in/out.  The two linear solves with S (:135, :139,
+// fullPivHouseholderQr in the reference) are done by Gaussian elimination with partial pivoting in long double: S is
+// symmetric positive definite, any backward-stable solver returns the same vectors to rounding.  (parity unpinned: the
+// reference's EKF needs Eigen and ROS headers and has no test vectors.)
+// ---------------------------------------------------------------------------------------------------------------------
+int oracle_ekf_init(const double* foot_pos_rel, const double* rot, double* x, double* P) {
+  for (int i = 0; i < 18 * 18; ++i) P[i] = 0.0;
+  for (int i = 0; i < 18; ++i) { P[i * 18 + i] = 3.0; x[i] = 0.0; }
+  x[2] = 0.09;
+  for (int leg = 0; leg < 4; ++leg)
+    for (int a = 0; a < 3; ++a)
+      x[6 + 3 * leg + a] = rot[3 * a] * foot_pos_rel[3 * leg] + rot[3 * a + 1] * foot_pos_rel[3 * leg + 1] + rot[3 * a + 2] * foot_pos_rel[3 * leg + 2] + x[a];
+  return 0;
+}
+
+int oracle_ekf_update(double dt, int assume_flat_ground, uint32_t movement_mode, const double* imu_acc, const double* imu_ang_vel,
+                      const double* rot, const double* foot_pos_rel, const double* foot_vel_rel, const double* foot_force, double* x, double* P,
+                      double* root_pos, double* root_lin_vel, uint32_t* est_contacts) {
+  constexpr int NX = 18, NY = 28;
+  typedef long double LD;
+  std::vector<LD> A(NX * NX, 0), Bm(NX * 3, 0), C(NY * NX, 0), Q(NX * NX, 0), Rn(NY * NY, 0);
+  for (int i = 0; i < NX; ++i) A[i * NX + i] = 1;
+  for (int i = 0; i < 4; ++i)
+    for (int a = 0; a < 3; ++a) {
+      C[(3 * i + a) * NX + a] = -1;                 // -pos
+      C[(3 * i + a) * NX + 6 + 3 * i + a] = 1;      // foot pos
+      C[(12 + 3 * i + a) * NX + 3 + a] = 1;         // vel
+    }
+  for (int i = 0; i < 4; ++i) C[(24 + i) * NX + 6 + 3 * i + 2] = 1;   // height z of foot
+  for (int a = 0; a < 3; ++a) { A[a * NX + 3 + a] = dt; Bm[(3 + a) * 3 + a] = dt; }
+  LD u[3];
+  for (int a = 0; a < 3; ++a) u[a] = (LD)rot[3 * a] * imu_acc[0] + (LD)rot[3 * a + 1] * imu_acc[1] + (LD)rot[3 * a + 2] * imu_acc[2];
+  u[2] += -9.81L;
+  double ec[4];
+  for (int i = 0; i < 4; ++i) ec[i] = (movement_mode == 0) ? 1.0 : std::min(std::max(foot_force[i] / (100.0 - 0.0), 0.0), 1.0);
+  for (int a = 0; a < 3; ++a) { Q[a * NX + a] = 0.01L * dt / 20.0L; Q[(3 + a) * NX + 3 + a] = 0.01L * dt * 9.8L / 20.0L; }
+  for (int i = 0; i < 4; ++i)
+    for (int a = 0; a < 3; ++a) {
+      const LD sc = 1 + (1 - (LD)ec[i]) * 1e3L;
+      Q[(6 + 3 * i + a) * NX + 6 + 3 * i + a] = sc * dt * 0.01L;
+      Rn[(3 * i + a) * NY + 3 * i + a] = sc * 0.001L;
+      Rn[(12 + 3 * i + a) * NY + 12 + 3 * i + a] = sc * 0.1L;
+    }
+  for (int i = 0; i < 4; ++i) Rn[(24 + i) * NY + 24 + i] = assume_flat_ground ? (1 + (1 - (LD)ec[i]) * 1e3L) * 0.001L : 1e5L;
+  // process update
+  std::vector<LD> xbar(NX, 0), AP(NX * NX, 0), Pbar(NX * NX, 0);
+  for (int i = 0; i < NX; ++i) {
+    LD s = 0;
+    for (int j = 0; j < NX; ++j) s += A[i * NX + j] * x[j];
+    for (int j = 0; j < 3; ++j) s += Bm[i * 3 + j] * u[j];
+    xbar[i] = s;
+  }
+  for (int i = 0; i < NX; ++i) for (int j = 0; j < NX; ++j) { LD s = 0; for (int k = 0; k < NX; ++k) s += A[i * NX + k] * P[k * NX + j]; AP[i * NX + j] = s; }
+  for (int i = 0; i < NX; ++i) for (int j = 0; j < NX; ++j) { LD s = Q[i * NX + j]; for (int k = 0; k < NX; ++k) s += AP[i * NX + k] * A[j * NX + k]; Pbar[i * NX + j] = s; }
+  // measurement
+  std::vector<LD> yhat(NY, 0), y(NY, 0), ey(NY, 0);
+  for (int r = 0; r < NY; ++r) { LD s = 0; for (int j = 0; j < NX; ++j) s += C[r * NX + j] * xbar[j]; yhat[r] = s; }
+  for (int i = 0; i < 4; ++i) {
+    const double* fk = foot_pos_rel + 3 * i;
+    LD sk[3] = {(LD)imu_ang_vel[1] * fk[2] - (LD)imu_ang_vel[2] * fk[1], (LD)imu_ang_vel[2] * fk[0] - (LD)imu_ang_vel[0] * fk[2],
+                (LD)imu_ang_vel[0] * fk[1] - (LD)imu_ang_vel[1] * fk[0]};
+    LD lv[3];
+    for (int a = 0; a < 3; ++a) lv[a] = -(LD)foot_vel_rel[3 * i + a] - sk[a];
+    for (int a = 0; a < 3; ++a) {
+      y[3 * i + a] = (LD)rot[3 * a] * fk[0] + (LD)rot[3 * a + 1] * fk[1] + (LD)rot[3 * a + 2] * fk[2];
+      const LD rl = (LD)rot[3 * a] * lv[0] + (LD)rot[3 * a + 1] * lv[1] + (LD)rot[3 * a + 2] * lv[2];
+      y[12 + 3 * i + a] = (1 - (LD)ec[i]) * x[3 + a] + (LD)ec[i] * rl;
+    }
+    y[24 + i] = (1 - (LD)ec[i]) * ((LD)x[2] + fk[2]) + (LD)ec[i] * 0;
+  }
+  for (int r = 0; r < NY; ++r) ey[r] = y[r] - yhat[r];
+  std::vector<LD> CP(NY * NX, 0), S(NY * NY, 0), PCt(NX * NY, 0);
+  for (int r = 0; r < NY; ++r) for (int j = 0; j < NX; ++j) { LD s = 0; for (int k = 0; k < NX; ++k) s += C[r * NX + k] * Pbar[k * NX + j]; CP[r * NX + j] = s; }
+  for (int j = 0; j < NX; ++j) for (int r = 0; r < NY; ++r) { LD s = 0; for (int k = 0; k < NX; ++k) s += Pbar[j * NX + k] * C[r * NX + k]; PCt[j * NY + r] = s; }
+  for (int r = 0; r < NY; ++r) for (int c = 0; c < NY; ++c) { LD s = Rn[r * NY + c]; for (int k = 0; k < NX; ++k) s += CP[r * NX + k] * C[c * NX + k]; S[r * NY + c] = s; }
+  { std::vector<LD> St(S); for (int r = 0; r < NY; ++r) for (int c = 0; c < NY; ++c) S[r * NY + c] = 0.5L * (St[r * NY + c] + St[c * NY + r]); }
+  // solve S [z | SC] = [ey | C]: elimination with partial pivoting on the augmented system
+  const int NR = 1 + NX;
+  std::vector<LD> M(NY * (NY + NR));
+  for (int r = 0; r < NY; ++r) {
+    for (int c = 0; c < NY; ++c) M[r * (NY + NR) + c] = S[r * NY + c];
+    M[r * (NY + NR) + NY] = ey[r];
+    for (int j = 0; j < NX; ++j) M[r * (NY + NR) + NY + 1 + j] = C[r * NX + j];
+  }
+  const int W = NY + NR;
+  for (int c = 0; c < NY; ++c) {
+    int pv = c;
+    for (int r = c + 1; r < NY; ++r) if (fabsl(M[r * W + c]) > fabsl(M[pv * W + c])) pv = r;
+    if (!(fabsl(M[pv * W + c]) > 0)) return 3;
+    if (pv != c) for (int k = 0; k < W; ++k) std::swap(M[c * W + k], M[pv * W + k]);
+    for (int r = c + 1; r < NY; ++r) {
+      const LD m = M[r * W + c] / M[c * W + c];
+      if (m != 0) for (int k = c; k < W; ++k) M[r * W + k] -= m * M[c * W + k];
+    }
+  }
+  std::vector<LD> Z(NY * NR);
+  for (int k = 0; k < NR; ++k)
+    for (int r = NY - 1; r >= 0; --r) {
+      LD s = M[r * W + NY + k];
+      for (int c = r + 1; c < NY; ++c) s -= M[r * W + c] * Z[c * NR + k];
+      Z[r * NR + k] = s / M[r * W + r];
+    }
+  // x = xbar + Pbar C' z ;  P = Pbar - Pbar C' SC Pbar ; symmetrise
+  std::vector<LD> xn(NX), T1(NX * NX, 0), Pn(NX * NX, 0);
+  for (int j = 0; j < NX; ++j) { LD s = xbar[j]; for (int r = 0; r < NY; ++r) s += PCt[j * NY + r] * Z[r * NR]; xn[j] = s; }
+  for (int i = 0; i < NX; ++i) for (int j = 0; j < NX; ++j) { LD s = 0; for (int r = 0; r < NY; ++r) s += PCt[i * NY + r] * Z[r * NR + 1 + j]; T1[i * NX + j] = s; }   // Pbar C' SC
+  for (int i = 0; i < NX; ++i) for (int j = 0; j < NX; ++j) { LD s = Pbar[i * NX + j]; for (int k = 0; k < NX; ++k) s -= T1[i * NX + k] * Pbar[k * NX + j]; Pn[i * NX + j] = s; }
+  std::vector<LD> Ps(NX * NX);
+  for (int i = 0; i < NX; ++i) for (int j = 0; j < NX; ++j) Ps[i * NX + j] = 0.5L * (Pn[i * NX + j] + Pn[j * NX + i]);
+  if (Ps[0] * Ps[NX + 1] - Ps[1] * Ps[NX] > 1e-6L) {
+    for (int i = 0; i < 2; ++i) for (int j = 2; j < NX; ++j) { Ps[i * NX + j] = 0; Ps[j * NX + i] = 0; }
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) Ps[i * NX + j] /= 10.0L;
+  }
+  for (int i = 0; i < NX; ++i) x[i] = (double)xn[i];
+  for (int i = 0; i < NX * NX; ++i) P[i] = (double)Ps[i];
+  if (est_contacts) { uint32_t m = 0; for (int i = 0; i < 4; ++i) m |= (ec[i] < 0.5 ? 0u : 1u) << i; *est_contacts = m; }
+  if (root_pos) for (int a = 0; a < 3; ++a) root_pos[a] = x[a];
+  if (root_lin_vel) for (int a = 0; a < 3; ++a) root_lin_vel[a] = x[3 + a];
+  return 0;
+}
+
 // wall-clock timing of the reference-faithful path (build + OSQP default, cold start) on nthreads
 double oracle_time_reference_path(const a1mpc_config* cfg, int B, const a1mpc_inputs* in, int nthreads, double* f_body) {
   auto t0 = std::chrono::steady_clock::now();

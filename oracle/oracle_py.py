@@ -164,6 +164,49 @@ def update_plan(gp, movement_mode, gait_counter, gait_counter_speed, lin_vel, li
     return gc, int(plan.value), sched, trel, tabs, tw
 
 
+def leg_kinematics(q, rho_opt, rho_fix):
+    """one leg: q[3], rho_opt[3], rho_fix[5] -> p[3], J[3,3] (J[a,k] = d p_a / d q_k)"""
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (q, rho_opt, rho_fix)]
+    p = np.zeros(3); J = np.zeros(9)
+    lib().oracle_leg_kinematics(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(p), _ptr(J))
+    return p, J.reshape(3, 3)
+
+
+def ref_leg_kinematics(q, rho_opt, rho_fix):
+    """the REFERENCE's own A1Kinematics::fk / jac, from oracle/_ref/libref_kin.so (`make -C oracle ref`; only where
+    /root/reference exists).  Returns None when that build is absent."""
+    so = os.path.join(_HERE, "_ref", "libref_kin.so")
+    if not os.path.exists(so):
+        return None
+    global _REFKIN
+    try:
+        _REFKIN
+    except NameError:
+        _REFKIN = C.CDLL(so)
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (q, rho_opt, rho_fix)]
+    p = np.zeros(3); J = np.zeros(9)
+    _REFKIN.ref_leg_kinematics(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(p), _ptr(J))
+    return p, J.reshape(3, 3)
+
+
+def ekf_init(foot_pos_rel, rot):
+    """one robot: foot_pos_rel[12] leg-major, rot[9] -> x[18], P[18,18]"""
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (foot_pos_rel, rot)]
+    x = np.zeros(18); P = np.zeros(324)
+    lib().oracle_ekf_init(_ptr(a[0]), _ptr(a[1]), _ptr(x), _ptr(P))
+    return x, P.reshape(18, 18)
+
+
+def ekf_update(x, P, dt, assume_flat_ground, movement_mode, imu_acc, imu_ang_vel, rot, foot_pos_rel, foot_vel_rel, foot_force):
+    """one robot, returns new x[18], P[18,18], root_pos, root_lin_vel, estimated_contacts mask, rc"""
+    x = np.array(x, dtype=np.float64); P = np.ascontiguousarray(np.array(P, dtype=np.float64).reshape(324))
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (imu_acc, imu_ang_vel, rot, foot_pos_rel, foot_vel_rel, foot_force)]
+    pos = np.zeros(3); vel = np.zeros(3); ec = C.c_uint32()
+    rc = lib().oracle_ekf_update(C.c_double(dt), int(assume_flat_ground), C.c_uint32(int(movement_mode)), *[_ptr(v) for v in a], _ptr(x), _ptr(P),
+                                 _ptr(pos), _ptr(vel), C.byref(ec))
+    return x, P.reshape(18, 18), pos, vel, int(ec.value), rc
+
+
 def time_reference_path(cfg, batch, nthreads):
     f = np.zeros((12, batch.B))
     inp = batch.c_inputs()

@@ -9,6 +9,7 @@
 #include <thread>
 
 #include "../../a1-qp-mpc-controller_b200/csrc/a1mpc_misc.cuh"
+#include "../../a1-qp-mpc-controller_b200/csrc/a1mpc_estim.cuh"
 #include "../../a1-qp-mpc-controller_b200/csrc/a1mpc_dense.cu"   // kernels only (host launchers are compiled out under A1MPC_EMU)
 
 using namespace a1mpc;
@@ -136,6 +137,42 @@ int emu_grf_qp(int B, const double* root_acc, const double* rot_z, const double*
   run_grf<3>(P, B, root_acc, rot_z, rot, foot, contact, list.data(), count, f_body, status, order_mode);
   run_grf<2>(P, B, root_acc, rot_z, rot, foot, contact, list.data(), count, f_body, status, order_mode);
   run_grf<1>(P, B, root_acc, rot_z, rot, foot, contact, list.data(), count, f_body, status, order_mode);
+  return 0;
+}
+
+// a1mpc_leg_kinematics_batch on the emulator
+int emu_leg_kinematics(int B, const double* joint_pos, const double* joint_vel, const double* rot, const double* rho_opt, const double* rho_fix,
+                       double* foot_pos_rel, double* jac, double* foot_vel_rel, double* foot_pos_abs, double* foot_vel_abs) {
+  LegParams P;
+  for (int i = 0; i < 12; ++i) P.rho_opt[i] = rho_opt[i];
+  for (int i = 0; i < 20; ++i) P.rho_fix[i] = rho_fix[i];
+  const int pb = 128, pgrid = (B + pb - 1) / pb;
+  for (int bx = 0; bx < pgrid; ++bx)
+    a1emu::run_block(a1emu::Dim3{(unsigned)bx, 0, 0}, a1emu::Dim3{(unsigned)pgrid, 1, 1}, pb, 0, 0,
+                     [&]() { leg_kinematics_kernel(B, joint_pos, joint_vel, rot, P, foot_pos_rel, jac, foot_vel_rel, foot_pos_abs, foot_vel_abs); });
+  return 0;
+}
+
+// a1mpc_ekf_init_batch / a1mpc_ekf_update_batch on the emulator (state: B x 342 doubles on the host)
+int emu_ekf_init(int B, double* state, const double* foot_pos_rel, const double* rot) {
+  const int pb = 128, pgrid = (B + pb - 1) / pb;
+  for (int bx = 0; bx < pgrid; ++bx)
+    a1emu::run_block(a1emu::Dim3{(unsigned)bx, 0, 0}, a1emu::Dim3{(unsigned)pgrid, 1, 1}, pb, 0, 0,
+                     [&]() { ekf_init_kernel(B, state, foot_pos_rel, rot); });
+  return 0;
+}
+
+int emu_ekf_update(int B, double* state, double dt, int assume_flat_ground, const uint32_t* movement_mode, const double* imu_acc,
+                   const double* imu_ang_vel, const double* rot, const double* foot_pos_rel, const double* foot_vel_rel, const double* foot_force,
+                   double* root_pos, double* root_lin_vel, uint32_t* est_contacts, int32_t* status, int order_mode) {
+  EkfParams P{dt, assume_flat_ground ? 1 : 0};
+  const int grid = std::max(1, (B + 2 * EKF_WPC - 1) / (2 * EKF_WPC));   // ~2 robots per warp: exercises the persistent loop
+  for (int bx = 0; bx < grid; ++bx)
+    a1emu::run_block(a1emu::Dim3{(unsigned)bx, 0, 0}, a1emu::Dim3{(unsigned)grid, 1, 1}, 32 * EKF_WPC, (size_t)EKF_WPC * EKF_WARP_DOUBLES * 8, order_mode,
+                     [&]() {
+                       ekf_update_kernel(B, P, state, movement_mode, imu_acc, imu_ang_vel, rot, foot_pos_rel, foot_vel_rel, foot_force, root_pos,
+                                         root_lin_vel, est_contacts, status);
+                     });
   return 0;
 }
 

@@ -66,3 +66,31 @@ def grf_qp(root_acc, rot_z, rot, foot, contact, order=0):
     f = np.zeros((B, 12)); status = np.full(B, -7, dtype=np.int32)
     assert lib().emu_grf_qp(B, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(contact), _p(f), _p(status), order) == 0
     return f, status
+
+
+def leg_kinematics(joint_pos, joint_vel, rot, rho_opt, rho_fix):
+    """a1mpc_leg_kinematics_batch on the emulator: [12,B], [12,B], [9,B] -> foot_pos_rel, jac [36,B], foot_vel_rel, foot_pos_abs, foot_vel_abs"""
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (joint_pos, joint_vel, rot, rho_opt, rho_fix)]
+    B = a[0].shape[1]
+    outs = [np.zeros((12, B)), np.zeros((36, B)), np.zeros((12, B)), np.zeros((12, B)), np.zeros((12, B))]
+    assert lib().emu_leg_kinematics(B, *[_p(v) for v in a], *[_p(o) for o in outs]) == 0
+    return outs
+
+
+def ekf_init(foot_pos_rel, rot):
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (foot_pos_rel, rot)]
+    B = a[0].shape[1]
+    state = np.zeros((B, 342))
+    assert lib().emu_ekf_init(B, _p(state), _p(a[0]), _p(a[1])) == 0
+    return state
+
+
+def ekf_update(state, dt, assume_flat_ground, movement_mode, imu_acc, imu_ang_vel, rot, foot_pos_rel, foot_vel_rel, foot_force, order=0):
+    """in place on state [B,342]; returns root_pos [3,B], root_lin_vel [3,B], estimated_contacts [B], status [B]"""
+    B = state.shape[0]
+    assert state.flags["C_CONTIGUOUS"] and state.dtype == np.float64
+    mm = np.ascontiguousarray(movement_mode, dtype=np.uint32)
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (imu_acc, imu_ang_vel, rot, foot_pos_rel, foot_vel_rel, foot_force)]
+    pos = np.zeros((3, B)); vel = np.zeros((3, B)); ec = np.zeros(B, dtype=np.uint32); status = np.full(B, -7, dtype=np.int32)
+    assert lib().emu_ekf_update(B, _p(state), C.c_double(dt), int(assume_flat_ground), _p(mm), *[_p(v) for v in a], _p(pos), _p(vel), _p(ec), _p(status), order) == 0
+    return pos, vel, ec, status

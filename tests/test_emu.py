@@ -181,3 +181,22 @@ def test_warm_start_across_ticks_on_emulator(E, a1, O):
     fact_warm = (it2 % 100 + it2 // 100)[nz & ~changed].mean()
     fact_cold = (it1 % 100 + it1 // 100)[nz].mean()
     assert fact_warm < 0.5 * fact_cold, (fact_warm, fact_cold)
+
+
+def test_leg_kinematics_and_ekf_on_emulator(E, O):
+    """SURVEY 8f.4 on the emulator: the batched FK/Jacobian kernel against the (reference-pinned) oracle, and 20 ticks of the
+    batched Kalman filter (DMMA Cholesky of the 28x28 innovation covariance, eight right-hand sides per solve) next to the
+    oracle's dense restatement, each carrying its own state"""
+    from common import check_kinematics, ekf_walk, estimation_scenario
+    rng, rho_opt, rho_fix, q, dq, rot = estimation_scenario(48, 1)
+    check_kinematics(O, E.leg_kinematics(q, dq, rot, rho_opt.reshape(12), rho_fix.reshape(20)), q, dq, rot, rho_opt, rho_fix)
+    box = {}
+
+    def init(fpr, rot_):
+        box["s"] = E.ekf_init(fpr, rot_)
+        return lambda: (box["s"][:, :18], box["s"][:, 18:].reshape(-1, 18, 18))
+
+    def update(dt, flat, mode, acc, gyro, rot_, fpr, fvr, force, tick):
+        return E.ekf_update(box["s"], dt, flat, mode, acc, gyro, rot_, fpr, fvr, force, order=tick % 3)
+    worst = ekf_walk(O, 40, 20, E.leg_kinematics, init, update, seed=2)
+    assert worst < 1e-11, worst

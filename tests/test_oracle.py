@@ -150,3 +150,34 @@ def test_neighbour_rows_oracle_sanity(O):
     f = np.arange(12.0); fk = np.ones(12) * 10
     tau = O.joint_torques(f, fk, jac, 0b0001, [0.1, 0.1, 0.1], np.zeros(12))
     assert np.allclose(tau[0:3], -2 * f[0:3]) and np.allclose(tau[3:], 0.5)
+
+
+def test_kinematics_oracle_is_pinned_to_the_reference(O):
+    """golden vectors generated from the REFERENCE's own A1Kinematics::fk / jac (tests/golden/make_kin_golden.py, built by
+    `make -C oracle ref` where /root/reference exists); and, when that build is present, a fresh random comparison"""
+    from common import load_kin_golden
+    g = load_kin_golden()
+    assert len(g["cases"]) >= 64
+    for c in g["cases"]:
+        p, J = O.leg_kinematics(c["q"], c["rho_opt"], c["rho_fix"])
+        assert np.abs(p - np.array(c["p"])).max() <= 1e-14 and np.abs(J.reshape(9) - np.array(c["J"])).max() <= 1e-14
+    rng = np.random.default_rng(7)
+    if O.ref_leg_kinematics(np.zeros(3), np.zeros(3), np.ones(5)) is not None:
+        for _ in range(500):
+            q = rng.uniform(-2, 2, 3); ro = rng.normal(0, 0.05, 3); rf = rng.normal(0, 0.2, 5)
+            pr, Jr = O.ref_leg_kinematics(q, ro, rf)
+            p, J = O.leg_kinematics(q, ro, rf)
+            assert np.abs(p - pr).max() <= 1e-14 and np.abs(J - Jr).max() <= 1e-14
+
+
+def test_ekf_oracle_sanity(O):
+    """the dense restatement of A1BasicEKF: a robot standing still on flat ground converges to the true height and zero velocity"""
+    rot = np.eye(3).reshape(9)
+    fk = np.array([[0.18, 0.13, -0.3], [0.18, -0.13, -0.3], [-0.18, 0.13, -0.3], [-0.18, -0.13, -0.3]]).reshape(12)
+    x, P = O.ekf_init(fk, rot)
+    assert np.allclose(np.diag(P), 3.0) and abs(x[2] - 0.09) < 1e-15 and np.allclose(x[6:9], fk[0:3] + [0, 0, 0.09])
+    for _ in range(400):
+        x, P, pos, vel, ec, rc = O.ekf_update(x, P, 0.0025, 1, 0, [0, 0, 9.81], [0, 0, 0], rot, fk, np.zeros(12), [80] * 4)
+        assert rc == 0 and ec == 0b1111
+    assert abs(pos[2] - 0.3) < 2e-3 and np.abs(vel).max() < 1e-3
+    assert np.allclose(P, P.T) and np.linalg.eigvalsh(P).min() > -1e-12
