@@ -31,10 +31,7 @@ def eng(a1):
 
 def test_leg_kinematics_golden_vectors_of_the_reference(a1, eng):
     g = load_kin_golden()["cases"]
-    B = len(g) // 4
-    q = np.zeros((12, B)); rho_opt = np.zeros(12); rho_fix = np.zeros(20)
-    # the golden cases cycle through the four legs; rho_opt differs per case, so run one batch column per case with that
-    # case's parameters on its own leg (batch-uniform parameters: one call per distinct rho_opt)
+    # rho_opt / rho_fix are batch-uniform parameters and differ from case to case: one call per golden case
     worst = 0.0
     for c in g:
         leg = c["leg"]
