@@ -4,11 +4,14 @@
 // as the checker by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs.  Nothing under a1-qp-mpc-controller_b200/ may include, link or call this file.
 //
-// PARITY UNPINNED: the reference holds no golden vector, known-answer test or fixture for this
+// PARITY UNPINNED (hot path, EKF): the reference holds no golden vector, known-answer test or fixture for this
 // path (test/test_mpc.cpp:157-161 prints and returns 0) and its arithmetic lives in third-party
 // OSQP (github.com/oxfordcontrol/osqp, unpinned master ~v0.6.2, docker/Dockerfile:77-83) behind
 // osqp-eigen (unpinned, build log 0.6.3, docker/Dockerfile:91-98); neither Eigen, OSQP nor ROS is
-// installable offline, so the reference itself cannot be compiled here (oracle/_ref is absent).
+// installable offline, so the reference's hot path cannot be compiled here.
+// PINNED (leg kinematics only): legKinematics/A1Kinematics.cpp compiles from where it lies against a stub of the three
+// Eigen types it touches (`make -C oracle ref` -> oracle/_ref/libref_kin.so); oracle_leg_kinematics agrees with it to
+// 2e-16 and tests/golden/kinematics_v1.json holds vectors generated from that build.
 // What pins this file instead: (1) two independent solvers below agree (OSQP-algorithm restatement
 // run to eps 1e-11 vs. long-double exact solver) and (2) every exact solution carries a KKT
 // certificate evaluated on the LITERAL 12N-variable problem, which is a proof of optimality that
