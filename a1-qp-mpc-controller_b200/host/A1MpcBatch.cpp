@@ -125,13 +125,18 @@ A1RobotControlBatch::A1RobotControlBatch(double mass, const double I[9], const d
   for (int i = 0; i < 9; ++i) cfg_.inertia[i] = I[i];
 }
 
-A1RobotControlBatch::~A1RobotControlBatch() { delete handle_; }
+A1RobotControlBatch::~A1RobotControlBatch() {
+  if (warm_ && handle_) a1mpc_device_free(handle_->h, warm_);
+  delete handle_;
+}
 
 void A1RobotControlBatch::compute_grf(const std::vector<A1CtrlStatesLite>& st, double dt, std::vector<std::array<double, 12>>& out,
                                       std::vector<int32_t>* status) {
   const size_t B = st.size();
   if (B == 0) { out.clear(); return; }
   if (!handle_ || dt != dt_) {  // mpc_dt is a handle-level constant (A1RobotControl.cpp:462-467)
+    if (warm_ && handle_) a1mpc_device_free(handle_->h, warm_);
+    warm_ = nullptr; warm_B_ = 0;
     delete handle_;
     handle_ = nullptr;
     cfg_.dt = dt;
@@ -158,7 +163,18 @@ void A1RobotControlBatch::compute_grf(const std::vector<A1CtrlStatesLite>& st, d
   }
   a1mpc_inputs in{x0_.data(), rot_.data(), foot_.data(), ref_.data(), contact_.data(), B};
   a1mpc_outputs o{f_.data(), status_.data(), nullptr, nullptr, B};
-  check(a1mpc_solve_batch(handle_->h, (int)B, &in, &o), "a1mpc_solve_batch");
+  if (warm_start_) {
+    if (warm_B_ != B) {   // a different batch: the slots mean different robots, start cold
+      if (warm_) a1mpc_device_free(handle_->h, warm_);
+      warm_ = nullptr;
+      check(a1mpc_device_alloc(handle_->h, a1mpc_warm_bytes(handle_->h, (int)B), &warm_), "a1mpc_device_alloc");
+      check(a1mpc_warm_reset(handle_->h, warm_, (int)B), "a1mpc_warm_reset");
+      warm_B_ = B;
+    }
+    check(a1mpc_solve_batch_warm(handle_->h, (int)B, &in, &o, warm_, 0), "a1mpc_solve_batch_warm");
+  } else {
+    check(a1mpc_solve_batch(handle_->h, (int)B, &in, &o), "a1mpc_solve_batch");
+  }
   out.resize(B);
   for (size_t b = 0; b < B; ++b)
     for (int leg = 0; leg < 4; ++leg)

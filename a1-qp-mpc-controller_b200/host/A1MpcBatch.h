@@ -86,12 +86,19 @@ class A1RobotControlBatch {
   // (A1RobotControl.cpp:563).  dt is mpc_dt when use_sim_time == "true" (A1RobotControl.cpp:465-467), else pass 0.0025.
   void compute_grf(const std::vector<A1CtrlStatesLite>& states, double dt, std::vector<std::array<double, 12>>& foot_forces_grf,
                    std::vector<int32_t>* status = nullptr);
+  // The reference's solver object persists and warm-starts every tick (A1RobotControl.h:67, A1RobotControl.cpp:522-538).
+  // true: robot b of consecutive compute_grf calls is the same robot, and its previous active faces are tried first
+  // (a1mpc_solve_batch_warm; horizon 10).  Off by default: batches of unrelated states gain nothing from it.
+  void set_warm_start(bool on) { warm_start_ = on; }
 
  private:
   a1mpc_config cfg_;
   int device_;
   double dt_ = -1.0;
   Handle* handle_ = nullptr;
+  bool warm_start_ = false;
+  void* warm_ = nullptr;      // device-resident warm-start state, owned by this object
+  size_t warm_B_ = 0;
   std::vector<double> x0_, rot_, foot_, ref_, f_;
   std::vector<uint32_t> contact_;
   std::vector<int32_t> status_;
