@@ -235,7 +235,7 @@ int a1mpc_create(a1mpc_handle** out, const a1mpc_config* cfg, int device) {
   P.N = cfg->horizon;
   P.max_iter = cfg->max_iter > 0 ? cfg->max_iter : 40;
   P.dt = cfg->dt; P.mu = cfg->mu; P.fzmax = cfg->fz_max; P.mass = cfg->mass;
-  P.mu_switch = cfg->tol > 0.0 ? cfg->tol : 1e-9;
+  P.mu_switch = cfg->tol > 0.0 ? cfg->tol : MU_SWITCH_DEFAULT;
   for (int i = 0; i < 9; ++i) P.inertia[i] = cfg->inertia[i];
   for (int i = 0; i < 13; ++i) P.q2[i] = 2.0 * cfg->q[i];
   for (int i = 0; i < 12; ++i) P.r2[i] = 2.0 * cfg->r[i];

@@ -21,7 +21,7 @@ DevParams make_params(const a1mpc_config* cfg) {   // a1mpc_create() in a1mpc_ap
   P.N = cfg->horizon;
   P.max_iter = cfg->max_iter > 0 ? cfg->max_iter : 40;
   P.dt = cfg->dt; P.mu = cfg->mu; P.fzmax = cfg->fz_max; P.mass = cfg->mass;
-  P.mu_switch = cfg->tol > 0.0 ? cfg->tol : 1e-9;
+  P.mu_switch = cfg->tol > 0.0 ? cfg->tol : MU_SWITCH_DEFAULT;
   for (int i = 0; i < 9; ++i) P.inertia[i] = cfg->inertia[i];
   for (int i = 0; i < 13; ++i) P.q2[i] = 2.0 * cfg->q[i];
   for (int i = 0; i < 12; ++i) P.r2[i] = 2.0 * cfg->r[i];

@@ -16,7 +16,7 @@ _LIBS = {}
 
 
 def lib(variant=""):
-    """variant "" = the product's default switches; "hyst" = -DA1MPC_FIN_HYST=1"""
+    """variant "" = the product's default switches; "nohyst" = -DA1MPC_FIN_HYST=0"""
     if variant not in _LIBS:
         name = "liba1mpc_emu%s.so" % ("_" + variant if variant else "")
         subprocess.check_call(["make", "-C", _HERE, "-s", name])
