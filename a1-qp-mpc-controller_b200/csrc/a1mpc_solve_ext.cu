@@ -9,12 +9,14 @@ namespace a1mpc {
 template <int N>
 static cudaError_t setup_n(int sm_count, ClassLaunch& c) {
   using G = Geo<4, N, 1>;
-  c.wpc = 1;
-  c.smem = G::smem_bytes(1);
-  cudaError_t e = cudaFuncSetAttribute(solve_kernel<4, N, 1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+  // N = 10: 4 warps per CTA like the other wrench-space classes (rendezvous before every factorisation); N = 20: one
+  constexpr int WPC = (N == 10) ? A1MPC_WPC34 : 1;
+  c.wpc = WPC;
+  c.smem = G::smem_bytes(WPC);
+  cudaError_t e = cudaFuncSetAttribute(solve_kernel<4, N, WPC, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<4, N, 1, 1, true>, 32, c.smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<4, N, WPC, 1, true>, 32 * WPC, c.smem);
   if (e != cudaSuccess) return e;
   if (occ < 1) return cudaErrorLaunchOutOfResources;
   c.max_ctas = occ * sm_count;
@@ -25,9 +27,10 @@ static cudaError_t setup_n(int sm_count, ClassLaunch& c) {
 cudaError_t ext_setup(int horizon, int sm_count, ClassLaunch& c) { return horizon == 10 ? setup_n<10>(sm_count, c) : setup_n<20>(sm_count, c); }
 
 void ext_launch(int horizon, const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count, const DevOutputs& out) {
-  int grid = B < c.max_ctas ? B : c.max_ctas;
+  int grid = (B + c.wpc - 1) / c.wpc;
+  if (grid > c.max_ctas) grid = c.max_ctas;
   if (grid < 1) grid = 1;
-  if (horizon == 10) solve_kernel<4, 10, 1, 1, true><<<grid, 32, c.smem, st>>>(P, rec, count, out);
+  if (horizon == 10) solve_kernel<4, 10, A1MPC_WPC34, 1, true><<<grid, 32 * A1MPC_WPC34, c.smem, st>>>(P, rec, count, out);
   else solve_kernel<4, 20, 1, 1, true><<<grid, 32, c.smem, st>>>(P, rec, count, out);
 }
 

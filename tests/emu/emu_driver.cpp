@@ -205,7 +205,7 @@ int emu_solve_batch(const a1mpc_config* cfg, int B, const a1mpc_inputs* in, cons
     if (cfg->horizon == 10) run_all<10>(P, rec.data(), cap, count, dout, order_mode, nthreads, st, warm, shift);
     else run_all<20>(P, rec.data(), cap, count, dout, order_mode, nthreads, st, nullptr, 0);
   } else {
-    if (cfg->horizon == 10) run_class<4, 10, 1, 1, true>(P, rec.data(), count, dout, order_mode, nthreads, st);
+    if (cfg->horizon == 10) run_class<4, 10, A1MPC_WPC34, 1, true>(P, rec.data(), count, dout, order_mode, nthreads, st);
     else run_class<4, 20, 1, 1, true>(P, rec.data(), count, dout, order_mode, nthreads, st);
   }
   if (stats) { stats[0] = st.collectives; stats[1] = st.mma; }
