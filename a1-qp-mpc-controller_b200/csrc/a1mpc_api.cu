@@ -39,6 +39,8 @@ struct a1mpc_handle {
   DevParams P;
   a1mpc::ClassLaunch cls[5];  // index = number of stance feet
   a1mpc::ClassLaunch cls_ext;  // extended path (config 4)
+  a1mpc::ClassLaunch cls_sched2;   // its compacted two-feet-per-step class (opt-in: A1MPC_EXT_COMPACT=1)
+  bool ext_compact = false;
   double* d_rec_ext = nullptr;
   size_t cap_ext = 0;
   uint32_t* d_sched = nullptr;
@@ -257,6 +259,14 @@ int a1mpc_create(a1mpc_handle** out, const a1mpc_config* cfg, int device) {
     if (e != cudaSuccess) return bail(fail(A1MPC_ECUDA, std::string("kernel setup: ") + cudaGetErrorString(e)));
     e = ext_setup(cfg->horizon, h->sm_count, h->cls_ext);
     if (e != cudaSuccess) return bail(fail(A1MPC_ECUDA, std::string("ext kernel setup: ") + cudaGetErrorString(e)));
+    {   // experimental this round (emulator-validated only): schedules with two stance feet per step on the compact direct kernel
+      const char* ev = std::getenv("A1MPC_EXT_COMPACT");
+      if (ev && ev[0] == '1' && cfg->horizon == 10) {
+        e = sched2_setup(h->sm_count, h->cls_sched2);
+        if (e != cudaSuccess) return bail(fail(A1MPC_ECUDA, std::string("compact ext kernel setup: ") + cudaGetErrorString(e)));
+        h->ext_compact = true;
+      }
+    }
     e = dense_setup(cfg->horizon);
     if (e != cudaSuccess) return bail(fail(A1MPC_ECUDA, std::string("dense kernel setup: ") + cudaGetErrorString(e)));
   }
@@ -366,7 +376,7 @@ int a1mpc_solve_batch_ext(a1mpc_handle* h, int B, const a1mpc_inputs* in, const 
     CK(cudaStreamSynchronize(h->stream));
     if (h->d_rec_ext) cudaFree(h->d_rec_ext);
     h->d_rec_ext = nullptr;
-    CK(cudaMalloc(&h->d_rec_ext, h->cap * REC_EXT_BYTES));
+    CK(cudaMalloc(&h->d_rec_ext, 2 * h->cap * REC_EXT_BYTES));   // second half: queue of the compacted class
     h->cap_ext = h->cap;
   }
   DevInputs di{in->x0, in->rot, in->foot, in->ref, in->contact, in->ld};
@@ -400,9 +410,16 @@ int a1mpc_solve_batch_ext(a1mpc_handle* h, int B, const a1mpc_inputs* in, const 
     dout = DevOutputs{h->d_f, h->d_status, out->iters ? h->d_iters : nullptr, out->u_full ? h->d_u : nullptr, Bs};
   }
   CK(cudaMemsetAsync(h->d_count, 0, 8 * sizeof(int), h->stream));
-  pack_ext_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(di, dsched, dnorm, B, h->d_rec_ext, h->d_count, dout, N);
-  ext_launch(N, h->cls_ext, h->stream, B, h->P, h->d_rec_ext, h->d_count, dout);
-  h->launches += 2;
+  if (h->ext_compact && dsched) {
+    pack_ext2_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(di, dsched, dnorm, B, h->d_rec_ext, (int)h->cap_ext, h->d_count, dout, N);
+    ext_launch(N, h->cls_ext, h->stream, B, h->P, h->d_rec_ext, h->d_count, dout);
+    sched2_launch(h->cls_sched2, h->stream, B, h->P, h->d_rec_ext + h->cap_ext * REC_EXT_DOUBLES, h->d_count, dout);
+    h->launches += 3;
+  } else {
+    pack_ext_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(di, dsched, dnorm, B, h->d_rec_ext, h->d_count, dout, N);
+    ext_launch(N, h->cls_ext, h->stream, B, h->P, h->d_rec_ext, h->d_count, dout);
+    h->launches += 2;
+  }
   CK(cudaGetLastError());
   if (!dev) {
     if ((rc = copy_rows(h->stream, out->f_body, out->ld, h->d_f, Bs, 12, Bs, 8, cudaMemcpyDeviceToHost))) return rc;

@@ -80,6 +80,53 @@ __global__ void pack_ext_kernel(DevInputs in, const uint32_t* __restrict__ sched
   }
 }
 
+// pack kernel of the extended path with the compacted class (A1MPC_EXT_COMPACT): schedules with exactly two stance feet in every
+// horizon step go to queue 6 (records behind the first `cap` records), everything else to queue 5 as in pack_ext_kernel
+__global__ void pack_ext2_kernel(DevInputs in, const uint32_t* __restrict__ sched, const double* __restrict__ normals, int B,
+                                 double* __restrict__ rec, int cap, int* __restrict__ count, DevOutputs out, int horizon) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  unsigned long long s0 = 0ull, s1 = 0ull;
+  bool two = true;
+  for (int st = 0; st < horizon; ++st) {
+    const unsigned long long m = (sched ? sched[(size_t)st * in.ld + b] : in.contact[b]) & 15u;
+    two = two && (__popc((unsigned)m) == 2);
+    if (st < 16) s0 |= m << (4 * st);
+    else s1 |= m << (4 * (st - 16));
+  }
+  if (s0 == 0ull && s1 == 0ull) {
+    for (int k = 0; k < 12; ++k) out.f_body[(size_t)k * out.ld + b] = 0.0;
+    out.status[b] = A1MPC_STATUS_NO_CONTACT;
+    if (out.iters) out.iters[b] = 0;
+    if (out.u_full)
+      for (int k = 0; k < 12 * horizon; ++k) out.u_full[(size_t)k * out.ld + b] = 0.0;
+    return;
+  }
+  const int slot = atomicAdd(&count[two ? 6 : 5], 1);
+  double* r = rec + ((two ? (size_t)cap : (size_t)0) + (size_t)slot) * REC_EXT_DOUBLES;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) r[k] = in.x0[(size_t)k * in.ld + b];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) r[12 + k] = in.rot[(size_t)k * in.ld + b];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) r[21 + k] = in.foot[(size_t)k * in.ld + b];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) r[33 + k] = in.ref[(size_t)k * in.ld + b];
+  r[42] = __hiloint2double((int)(s0 & 15ull), b);
+  r[43] = 0.0;
+  r[44] = __longlong_as_double((long long)s0);
+  r[45] = __longlong_as_double((long long)s1);
+  for (int leg = 0; leg < 4; ++leg) {
+    double nx = 0.0, ny = 0.0, nz = 1.0;
+    if (normals) {
+      nx = normals[(size_t)(3 * leg) * in.ld + b]; ny = normals[(size_t)(3 * leg + 1) * in.ld + b]; nz = normals[(size_t)(3 * leg + 2) * in.ld + b];
+      const double inv = rsqrt(nx * nx + ny * ny + nz * nz);
+      nx *= inv; ny *= inv; nz *= inv;
+    }
+    r[46 + 3 * leg] = nx; r[47 + 3 * leg] = ny; r[48 + 3 * leg] = nz;
+  }
+}
+
 // Classes whose factor does not fit in shared memory (N=20 with four stance feet in fp64):
 // reported, never silently approximated.
 __global__ void unsupported_kernel(const double* __restrict__ rec, const int* __restrict__ count, int cls, DevOutputs out, int horizon) {

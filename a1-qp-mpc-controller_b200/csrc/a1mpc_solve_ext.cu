@@ -3,6 +3,7 @@
 // It is the 4-foot wrench-space kernel with absent foot-steps pinned to zero (identity rows), forces solved in each
 // foot's terrain frame.
 #include "a1mpc_internal.h"
+#include "a1mpc_sched.cuh"
 
 namespace a1mpc {
 
@@ -32,6 +33,28 @@ void ext_launch(int horizon, const ClassLaunch& c, cudaStream_t st, int B, const
   if (grid < 1) grid = 1;
   if (horizon == 10) solve_kernel<4, 10, A1MPC_WPC34, 1, true><<<grid, 32 * A1MPC_WPC34, c.smem, st>>>(P, rec, count, out);
   else solve_kernel<4, 20, 1, 1, true><<<grid, 32, c.smem, st>>>(P, rec, count, out);
+}
+
+cudaError_t sched2_setup(int sm_count, ClassLaunch& c) {
+  constexpr int WPC = 4;
+  c.wpc = WPC;
+  c.smem = SchedGeo<10>::smem_bytes(WPC);
+  cudaError_t e = cudaFuncSetAttribute(solve_kernel_sched2<10, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel_sched2<10, WPC>, 32 * WPC, c.smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorLaunchOutOfResources;
+  c.max_ctas = occ * sm_count;
+  c.supported = true;
+  return cudaSuccess;
+}
+
+void sched2_launch(const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count, const DevOutputs& out) {
+  int grid = (B + c.wpc - 1) / c.wpc;
+  if (grid > c.max_ctas) grid = c.max_ctas;
+  if (grid < 1) grid = 1;
+  solve_kernel_sched2<10, 4><<<grid, 32 * 4, c.smem, st>>>(P, rec, count, out);
 }
 
 }  // namespace a1mpc

@@ -10,6 +10,7 @@
 
 #include "../../a1-qp-mpc-controller_b200/csrc/a1mpc_misc.cuh"
 #include "../../a1-qp-mpc-controller_b200/csrc/a1mpc_estim.cuh"
+#include "../../a1-qp-mpc-controller_b200/csrc/a1mpc_sched.cuh"
 #include "../../a1-qp-mpc-controller_b200/csrc/a1mpc_dense.cu"   // kernels only (host launchers are compiled out under A1MPC_EMU)
 
 using namespace a1mpc;
@@ -137,6 +138,41 @@ int emu_grf_qp(int B, const double* root_acc, const double* rot_z, const double*
   run_grf<3>(P, B, root_acc, rot_z, rot, foot, contact, list.data(), count, f_body, status, order_mode);
   run_grf<2>(P, B, root_acc, rot_z, rot, foot, contact, list.data(), count, f_body, status, order_mode);
   run_grf<1>(P, B, root_acc, rot_z, rot, foot, contact, list.data(), count, f_body, status, order_mode);
+  return 0;
+}
+
+// the compacted two-feet-per-step kernel of a1mpc_sched.cuh; every QP of the batch must have exactly two stance feet in every step
+int emu_solve_sched2(const a1mpc_config* cfg, int B, const a1mpc_inputs* in, const uint32_t* sched, const double* normals,
+                     const a1mpc_outputs* o, int order_mode, int nthreads) {
+  if (cfg->horizon != 10 || !sched) return -1;
+  for (int st = 0; st < 10; ++st)
+    for (int b = 0; b < B; ++b)
+      if (__builtin_popcount(sched[(size_t)st * in->ld + b] & 15u) != 2) return -2;
+  const DevParams P = make_params(cfg);
+  const DevInputs din{in->x0, in->rot, in->foot, in->ref, in->contact, in->ld};
+  const DevOutputs dout{o->f_body, o->status, o->iters, o->u_full, o->ld};
+  int count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::vector<double> rec((size_t)B * REC_EXT_DOUBLES + 2);
+  const int pb = 128, pgrid = (B + pb - 1) / pb;
+  for (int bx = 0; bx < pgrid; ++bx)
+    a1emu::run_block(a1emu::Dim3{(unsigned)bx, 0, 0}, a1emu::Dim3{(unsigned)pgrid, 1, 1}, pb, 0, 0,
+                     [&]() { pack_ext_kernel(din, sched, normals, B, rec.data(), count, dout, cfg->horizon); });
+  count[6] = count[5];
+  constexpr int WPC = 4;
+  const int nq = count[6], grid = std::max(1, (nq + 2 * WPC - 1) / (2 * WPC));
+  std::atomic<int> next{0};
+  auto worker = [&]() {
+    for (;;) {
+      const int bx = next.fetch_add(1);
+      if (bx >= grid) break;
+      a1emu::run_block(a1emu::Dim3{(unsigned)bx, 0, 0}, a1emu::Dim3{(unsigned)grid, 1, 1}, 32 * WPC, SchedGeo<10>::smem_bytes(WPC), order_mode,
+                       [&]() { solve_kernel_sched2<10, WPC>(P, rec.data(), count, dout); });
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < std::max(1, nthreads); ++t) th.emplace_back(worker);
+  worker();
+  for (auto& t : th) t.join();
   return 0;
 }
 

@@ -94,3 +94,19 @@ def ekf_update(state, dt, assume_flat_ground, movement_mode, imu_acc, imu_ang_ve
     pos = np.zeros((3, B)); vel = np.zeros((3, B)); ec = np.zeros(B, dtype=np.uint32); status = np.full(B, -7, dtype=np.int32)
     assert lib().emu_ekf_update(B, _p(state), C.c_double(dt), int(assume_flat_ground), _p(mm), *[_p(v) for v in a], _p(pos), _p(vel), _p(ec), _p(status), order) == 0
     return pos, vel, ec, status
+
+
+def solve_sched2(cfg, st, sched, normals=None, order=0, nthreads=8, want_u=False):
+    """the compacted two-stance-feet-per-step kernel (a1mpc_sched.cuh); same contract as solve(..., sched=...)"""
+    B = st["contact"].shape[0]
+    arrs = [np.ascontiguousarray(st[k], dtype=np.float64) for k in ("x0", "rot", "foot", "ref")]
+    contact = np.ascontiguousarray(st["contact"], dtype=np.uint32)
+    inp = a1mpc.Inputs(_p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(contact), B)
+    f = np.zeros((12, B)); status = np.full(B, -7, dtype=np.int32); iters = np.zeros(B, dtype=np.int32)
+    u = np.zeros((12 * cfg.horizon, B)) if want_u else None
+    out = a1mpc.Outputs(_p(f), _p(status), _p(iters), _p(u), B)
+    sc = np.ascontiguousarray(sched, dtype=np.uint32)
+    nm = np.ascontiguousarray(normals, dtype=np.float64) if normals is not None else None
+    rc = lib().emu_solve_sched2(C.byref(cfg), B, C.byref(inp), _p(sc), _p(nm), C.byref(out), order, nthreads)
+    assert rc == 0, rc
+    return (f, status, iters, u) if want_u else (f, status, iters)

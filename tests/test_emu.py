@@ -198,3 +198,17 @@ def test_leg_kinematics_and_ekf_on_emulator(E, O):
         return E.ekf_update(box["s"], dt, flat, mode, acc, gyro, rot_, fpr, fvr, force, order=tick % 3)
     worst = ekf_walk(O, 40, 20, E.leg_kinematics, init, update, seed=2)
     assert worst < 1e-11, worst
+
+
+def test_compact_two_feet_schedule_kernel_on_emulator(E, a1, O):
+    """a1mpc_sched.cuh: config-4 schedules with two stance feet per step as a 60-variable direct problem (legs change from step
+    to step; full 12x12 Gram blocks + (step, leg) selection), with and without terrain normals, against the extended oracle"""
+    B = 120
+    st = a1.gen_states(B, 4, 55)
+    sched, normals = a1.gen_schedule(B, 10, 4, 55)
+    assert all(bin(int(m) & 15).count("1") == 2 for m in sched.reshape(-1))      # trot / bound / gallop phases of the generator
+    cfg = a1.default_config(horizon=10)
+    for nm in (normals, None):
+        f, status, iters, u = E.solve_sched2(cfg, st, sched, nm, order=2, want_u=True)
+        fo, info, uo = O.compute_grf_batch_ext(O.make_config(horizon=10), obatch(O, st), sched, nm, mode=O.MODE_EXACT, nthreads=4, want_u=True)
+        assert (status == a1.STATUS_OPTIMAL).all() and np.abs(f - fo).max() < 1e-7 and np.abs(u.T - uo).max() < 1e-7
