@@ -12,3 +12,5 @@ for v in r1algo ffrag; do [ -f ab/liba1mpc_$v.so ] && { echo "== $v"; A1MPC_LIB=
 timeout 100 python tools/hard_qp.py | tee gpurun_out/r02_hard_qp.txt
 timeout 160 python tools/robust_sweep.py | tee gpurun_out/r02_robust.txt
 for n in 0.0 0.1 0.3; do timeout 100 python tools/warm_bench.py 1024 $n; timeout 100 python tools/warm_bench.py 16384 $n; done | tee gpurun_out/r02_warm.txt
+echo "== config 4, general extended kernel"; timeout 200 python tools/ext_probe.py | tee gpurun_out/r02_ext.txt
+echo "== config 4, compacted class (A1MPC_EXT_COMPACT=1)"; A1MPC_EXT_COMPACT=1 timeout 200 python tools/ext_probe.py | tee gpurun_out/r02_ext_compact.txt
