@@ -31,6 +31,7 @@ a1emu_switch:
 namespace a1emu {
 
 thread_local Block* g_blk = nullptr;
+thread_local int g_f32 = 0;
 
 void yield_to_scheduler() {
   Block& b = *g_blk;

@@ -65,6 +65,7 @@ struct Block {
 };
 
 extern thread_local Block* g_blk;
+extern thread_local int g_f32;   // experiment (A1MPC_EMU_F32): > 0 while a factorisation runs whose arithmetic is rounded to fp32
 void yield_to_scheduler();
 // runs `body` once per thread of one block (threadIdx/blockDim set), with dynamic shared memory of smem_bytes
 void run_block(Dim3 block_idx, Dim3 grid_dim, int nthreads, size_t smem_bytes, int order_mode, const std::function<void()>& body,
@@ -161,9 +162,11 @@ inline void a1emu_dmma884(double& d0, double& d1, double a, double b, double c0,
   for (int k = 0; k < 4; ++k) {
     const double av = a1emu::u2d(w.slot[g & 1][row * 4 + k]);
     const double b0 = a1emu::u2d(w.slot2[g & 1][col * 4 + k]), b1 = a1emu::u2d(w.slot2[g & 1][(col + 1) * 4 + k]);
-    if (model == 0) { r0 = std::fma(av, b0, r0); r1 = std::fma(av, b1, r1); }
+    if (a1emu::g_f32 > 0) { r0 = (double)((float)r0 + (float)av * (float)b0); r1 = (double)((float)r1 + (float)av * (float)b1); }
+    else if (model == 0) { r0 = std::fma(av, b0, r0); r1 = std::fma(av, b1, r1); }
     else { volatile double q0 = av * b0, q1 = av * b1; p0[k] = q0; p1[k] = q1; }
   }
+  if (a1emu::g_f32 > 0) { d0 = r0; d1 = r1; return; }
   if (model == 1) { for (int k = 0; k < 4; ++k) { r0 += p0[k]; r1 += p1[k]; } }
   if (model == 2) { r0 += (p0[0] + p0[1]) + (p0[2] + p0[3]); r1 += (p1[0] + p1[1]) + (p1[2] + p1[3]); }
   // the operands of this collective stay valid until every lane has arrived at the NEXT one, so no second barrier
