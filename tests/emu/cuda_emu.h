@@ -66,6 +66,15 @@ struct Block {
 
 extern thread_local Block* g_blk;
 extern thread_local int g_f32;   // experiment (A1MPC_EMU_F32): > 0 while a factorisation runs whose arithmetic is rounded to fp32
+// round to A1EMU_MANT mantissa bits (environment; default 23 = fp32, 10 = tf32, 7 = bf16) -- experiment only
+inline double lowp(double x) {
+  static const int mant = std::getenv("A1EMU_MANT") ? std::atoi(std::getenv("A1EMU_MANT")) : 23;
+  if (mant >= 23) return (double)(float)x;
+  if (x == 0.0 || !(x == x)) return x;
+  int e;
+  const double m = std::frexp(x, &e);
+  return std::ldexp(std::nearbyint(std::ldexp(m, mant + 1)), e - mant - 1);
+}
 void yield_to_scheduler();
 // runs `body` once per thread of one block (threadIdx/blockDim set), with dynamic shared memory of smem_bytes
 void run_block(Dim3 block_idx, Dim3 grid_dim, int nthreads, size_t smem_bytes, int order_mode, const std::function<void()>& body,
@@ -162,7 +171,9 @@ inline void a1emu_dmma884(double& d0, double& d1, double a, double b, double c0,
   for (int k = 0; k < 4; ++k) {
     const double av = a1emu::u2d(w.slot[g & 1][row * 4 + k]);
     const double b0 = a1emu::u2d(w.slot2[g & 1][col * 4 + k]), b1 = a1emu::u2d(w.slot2[g & 1][(col + 1) * 4 + k]);
-    if (a1emu::g_f32 > 0) { r0 = (double)((float)r0 + (float)av * (float)b0); r1 = (double)((float)r1 + (float)av * (float)b1); }
+    if (a1emu::g_f32 > 0) {   // low-precision inputs, fp32 accumulation (what a tf32 / bf16 MMA does)
+      r0 = (double)((float)r0 + (float)(a1emu::lowp(av) * a1emu::lowp(b0))); r1 = (double)((float)r1 + (float)(a1emu::lowp(av) * a1emu::lowp(b1)));
+    }
     else if (model == 0) { r0 = std::fma(av, b0, r0); r1 = std::fma(av, b1, r1); }
     else { volatile double q0 = av * b0, q1 = av * b1; p0[k] = q0; p1[k] = q1; }
   }
