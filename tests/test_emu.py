@@ -212,3 +212,23 @@ def test_compact_two_feet_schedule_kernel_on_emulator(E, a1, O):
         f, status, iters, u = E.solve_sched2(cfg, st, sched, nm, order=2, want_u=True)
         fo, info, uo = O.compute_grf_batch_ext(O.make_config(horizon=10), obatch(O, st), sched, nm, mode=O.MODE_EXACT, nthreads=4, want_u=True)
         assert (status == a1.STATUS_OPTIMAL).all() and np.abs(f - fo).max() < 1e-7 and np.abs(u.T - uo).max() < 1e-7
+
+
+def test_edge_cases_on_emulator(E, a1, O):
+    """NaN / Inf inputs, no stance foot, bits above the four legs -- statuses and zero forces, neighbours unaffected; the same through
+    the warm-start kernels (a robot that was NUMERICAL stores no guess)"""
+    st = a1.gen_states(40, 2, 51)
+    st["contact"][0] = 0
+    st["contact"][1] = 0b10000
+    st["x0"][5, 2] = np.nan
+    st["foot"][3, 3] = np.inf
+    cfg = a1.default_config(horizon=10)
+    warm = np.zeros((40, 44), dtype=np.uint32)
+    for kw in ({}, {"warm": warm, "shift": 0}):
+        f, status, iters, _ = E.solve(cfg, st, **kw)
+        assert status[0] == a1.STATUS_NO_CONTACT and status[1] == a1.STATUS_NO_CONTACT and np.abs(f[:, :2]).max() == 0
+        assert status[2] == a1.STATUS_NUMERICAL and status[3] == a1.STATUS_NUMERICAL and np.abs(f[:, 2:4]).max() == 0
+        ok = np.arange(40) >= 4
+        fo, info = O.compute_grf_batch(O.make_config(), obatch(O, st, slice(4, 40)), O.MODE_EXACT, nthreads=4)
+        assert (status[ok] == 0).all() and np.abs(f[:, ok] - fo).max() <= TOL_F
+    assert (warm[2:4, 0] == 0).all() and (warm[4:, 0] == 1).all()
