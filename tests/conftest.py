@@ -56,6 +56,11 @@ if os.environ.get("A1MPC_EMU_ENGINE") == "1":
     sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
     import ctypes as _C
 
+    import a1mpc as _a1probe
+    if _a1probe.lib().a1mpc_device_count() > 0:
+        # never let the replay stand in for the real thing: with a GPU present the `-m gpu` suite must run the CUDA library
+        raise pytest.UsageError("A1MPC_EMU_ENGINE=1 is a CPU-only development aid; a CUDA device is visible -- unset it")
+
     import numpy as _np
 
     import a1mpc as _a1
