@@ -90,6 +90,15 @@ def lib():
         l.a1mpc_event_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         l.a1mpc_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         l.a1mpc_solve_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Inputs), C.POINTER(Outputs)]
+        l.a1mpc_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Config), C.c_int]
+        l.a1mpc_default_config.argtypes = [C.POINTER(Config)]
+        l.a1mpc_warm_bytes.argtypes = [C.c_void_p, C.c_int]
+        l.a1mpc_warm_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        l.a1mpc_solve_batch_warm.argtypes = [C.c_void_p, C.c_int, C.POINTER(Inputs), C.POINTER(Outputs), C.c_void_p, C.c_int]
+        l.a1mpc_leg_kinematics_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 10
+        l.a1mpc_ekf_bytes.argtypes = [C.c_int]
+        l.a1mpc_ekf_init_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.a1mpc_ekf_update_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_int] + [C.c_void_p] * 11
         l.a1mpc_solve_batch_ext.argtypes = [C.c_void_p, C.c_int, C.POINTER(Inputs), C.POINTER(InputsExt), C.POINTER(Outputs)]
         l.a1mpc_gen_schedule.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         l.a1mpc_build_qp_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Inputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

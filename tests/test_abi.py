@@ -71,3 +71,39 @@ def test_generator_is_deterministic_and_well_formed(a1):
     # the first 16 QPs of a batch do not depend on the batch size (per-QP substreams)
     s = a1.gen_states(16, 2, 5)
     assert np.array_equal(s["x0"], a["x0"][:, :16])
+
+
+def test_every_binding_marshals_its_arguments(a1):
+    """Every Engine method of a1mpc.py, driven with a NULL handle: the C entry points must reject it with A1MPC_EINVAL
+    *after* ctypes has converted every argument against the declared prototype -- a wrong argument count or type in the
+    binding shows up here (ctypes.ArgumentError / TypeError) instead of on the GPU box."""
+    eng = a1.Engine.__new__(a1.Engine)
+    eng.h, eng.cfg, eng.device = None, a1.default_config(), 0
+    B = 4
+    st = a1.gen_states(B, 2, 1)
+    null = C.c_void_p(0)
+    rng = np.random.default_rng(0)
+    r = lambda *s: rng.standard_normal(s)
+    calls = [
+        lambda: eng.solve(st, want_u=True),
+        lambda: eng.solve_warm(st, null),
+        lambda: eng.warm_alloc(B),
+        lambda: eng.solve_ext(st, np.full((10, B), 9, dtype=np.uint32), np.tile([0.0, 0.0, 1.0], 4)[:, None].repeat(B, 1)),
+        lambda: eng.build_qp(st),
+        lambda: eng.qp_mats(r(B, 13, 13), r(B, 130, 12), r(B, 13), r(B, 130)),
+        lambda: eng.solve_dense(r(B, 120, 120), r(B, 120), np.full(B, 9, dtype=np.uint32)),
+        lambda: eng.grf_qp(r(B, 6), r(B, 9), r(B, 9), r(B, 12), np.full(B, 15, dtype=np.uint32)),
+        lambda: eng.leg_kinematics(r(12, B), r(12, B), r(9, B), r(12), r(20)),
+        lambda: eng.ekf_alloc(B),
+        lambda: eng.ekf_init(null, r(12, B), r(9, B)),
+        lambda: eng.ekf_update(null, 0.0025, True, np.ones(B, dtype=np.uint32), r(3, B), r(3, B), r(9, B), r(12, B), r(12, B), r(4, B)),
+        lambda: eng.ekf_state(null, B),
+        lambda: eng.update_plan(a1.default_gait_params(10), r(4, B), r(4, B), np.ones(B, dtype=np.uint32), r(3, B), r(3, B), r(9, B), r(9, B), r(3, B)),
+        lambda: eng.dalloc(64),
+        lambda: eng.halloc(64),
+    ]
+    for i, call in enumerate(calls):
+        with pytest.raises(a1.A1MpcError):
+            call()
+    assert a1.lib().a1mpc_warm_bytes(None, B) == 0 and a1.lib().a1mpc_ekf_bytes(B) == B * 342 * 8
+    eng.h = None   # nothing to destroy
