@@ -131,7 +131,8 @@ def test_degenerate_vertex_family_is_certified_thanks_to_hysteresis(E, a1, O):
     """The one QP of the 1.44 M robustness sweep on the B200 (profiles/r01d_robust_sweep_dmma.txt) that ended IPM_ONLY, with
     1e-9 perturbations: at one foot-step the optimum is the cone vertex with a degenerate multiplier; release (dual violation
     4e-11, just above the 1e-11 certificate tolerance) and re-pin (fz = -2.6e-7) alternated for all 36 rounds.  Without the
-    finisher hysteresis the status says so (never a silent wrong answer); with it (the default) every copy is certified."""
+    finisher's safeguards (hysteresis, escalating refinement: variant "nohyst") the status says so -- never a silent wrong
+    answer; with them (the default) every copy is certified."""
     d = dict(np.load(os.path.join(ROOT, "tools", "data", "hard_qp_63168.npz")))
     n = 96
     rng = np.random.default_rng(3)
@@ -144,6 +145,20 @@ def test_degenerate_vertex_family_is_certified_thanks_to_hysteresis(E, a1, O):
     f0, status0, iters0, _ = E.solve(cfg, st, variant="nohyst")
     assert set(np.unique(status0)) == {a1.STATUS_OPTIMAL, a1.STATUS_IPM_ONLY}            # the cycle, reported as such
     assert np.abs(f0 - fo)[:, status0 == a1.STATUS_OPTIMAL].max() < 1e-7 and np.abs(f0 - fo).max() < 1e-2
+
+
+def test_false_dual_violation_from_an_under_refined_solve(E, a1, O):
+    """QP 618 of an emulator sweep (config 4, seed 777, three stance feet): the wrench-space reduced system of the finisher,
+    refined once, left 1e-7 of residual on a free coordinate; that showed up as a dual violation of 4e-7 at a foot-step whose
+    optimum IS the cone vertex -- release, primal violation (fz = -2e-4), re-pin, for all 36 rounds, status IPM_ONLY and 2e-3 N
+    off.  From the fourth round of a guess the solves get two more refinement steps: verified in round 5."""
+    d = dict(np.load(os.path.join(ROOT, "tools", "data", "hard_qp_777_618.npz")))
+    cfg = a1.default_config(horizon=10)
+    fo, info = O.compute_grf_batch(O.make_config(horizon=10), obatch(O, d), mode=O.MODE_EXACT, nthreads=1)
+    f, status, iters, _ = E.solve(cfg, d)
+    assert status[0] == a1.STATUS_OPTIMAL and np.abs(f - fo).max() < 1e-7 and iters[0] // 100 <= 6
+    f0, status0, iters0, _ = E.solve(cfg, d, variant="nohyst")
+    assert status0[0] == a1.STATUS_IPM_ONLY and iters0[0] // 100 == 36 and 1e-4 < np.abs(f0 - fo).max() < 1e-2
 
 
 def test_warm_start_across_ticks_on_emulator(E, a1, O):
