@@ -10,7 +10,7 @@ echo "== base"; timeout 200 python tools/perf_quick.py 10 | tee gpurun_out/r02_b
 for v in r1algo ffrag rsqrtlib fixedref; do [ -f ab/liba1mpc_$v.so ] && { echo "== $v"; A1MPC_LIB=$PWD/ab/liba1mpc_$v.so timeout 200 python tools/perf_quick.py 10 | tee gpurun_out/r02_$v.txt; }; done
 [ -f ab/liba1mpc_sswitch.so ] && { echo "== sswitch (N=20)"; A1MPC_LIB=$PWD/ab/liba1mpc_sswitch.so timeout 200 python tools/perf_quick.py 20 | tee gpurun_out/r02_sswitch20.txt; }
 timeout 100 python tools/hard_qp.py | tee gpurun_out/r02_hard_qp.txt
-timeout 160 python tools/robust_sweep.py | tee gpurun_out/r02_robust.txt
+timeout 400 python tools/robust_sweep.py | tee gpurun_out/r02_robust.txt
 for n in 0.0 0.1 0.3; do timeout 100 python tools/warm_bench.py 1024 $n; timeout 100 python tools/warm_bench.py 16384 $n; done | tee gpurun_out/r02_warm.txt
 echo "== config 4, general extended kernel"; timeout 200 python tools/ext_probe.py | tee gpurun_out/r02_ext.txt
 echo "== config 4, compacted class (A1MPC_EXT_COMPACT=1)"; A1MPC_EXT_COMPACT=1 timeout 200 python tools/ext_probe.py | tee gpurun_out/r02_ext_compact.txt
