@@ -4,18 +4,20 @@
 // as the checker by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs.  Nothing under a1-qp-mpc-controller_b200/ may include, link or call this file.
 //
-// PARITY UNPINNED (hot path, EKF): the reference holds no golden vector, known-answer test or fixture for this
-// path (test/test_mpc.cpp:157-161 prints and returns 0) and its arithmetic lives in third-party
-// OSQP (github.com/oxfordcontrol/osqp, unpinned master ~v0.6.2, docker/Dockerfile:77-83) behind
-// osqp-eigen (unpinned, build log 0.6.3, docker/Dockerfile:91-98); neither Eigen, OSQP nor ROS is
-// installable offline, so the reference's hot path cannot be compiled here.
-// PINNED (leg kinematics only): legKinematics/A1Kinematics.cpp compiles from where it lies against a stub of the three
-// Eigen types it touches (`make -C oracle ref` -> oracle/_ref/libref_kin.so); oracle_leg_kinematics agrees with it to
-// 2e-16 and tests/golden/kinematics_v1.json holds vectors generated from that build.
-// What pins this file instead: (1) two independent solvers below agree (OSQP-algorithm restatement
-// run to eps 1e-11 vs. long-double exact solver) and (2) every exact solution carries a KKT
-// certificate evaluated on the LITERAL 12N-variable problem, which is a proof of optimality that
-// does not depend on how the point was found (H is positive definite: 2r > 0).
+// PARITY PINNED to the reference's own compiled code (everything but the third-party OSQP iteration):
+// the reference's ConvexMpc.cpp, A1RobotControl.cpp, A1BasicEKF.cpp, utils/Utils.cpp and legKinematics/A1Kinematics.cpp compile
+// UNMODIFIED, from where they lie under /root/reference, against the header stand-ins of oracle/ref_shim/ (a small API-compatible
+// subset of Eigen, plus inert OsqpEigen / ROS stubs; Eigen, OSQP and ROS are not installable offline) -- `make -C oracle ref` ->
+// oracle/_ref/libref_mpc.so, libref_kin.so and ref_test_mpc (the reference's test/test_mpc.cpp, main() and all).  Against that
+// build this file agrees to <= 2e-15 relative on H, g, A_qp, B_qp, x_d, bit-exactly on lb, ub, the pyramid matrix and x0, on the
+// single-step QP set-up, compute_joint_torques, update_plan, and to 1e-11 over 30 ticks of A1BasicEKF (tests/test_ref_pin.py);
+// tests/golden/convexmpc_v1.npz carries vectors generated from that build to the GPU box (tests/golden/make_ref_golden.py).
+// What cannot be pinned: OSQP's ADMM iterates (github.com/oxfordcontrol/osqp, unpinned master ~v0.6.2, docker/Dockerfile:77-83,
+// behind osqp-eigen 0.6.3, docker/Dockerfile:91-98 -- neither vendored).  The reference holds no golden vector for the solve
+// (test/test_mpc.cpp:157-161 prints and returns 0).  The QP is strictly convex (2r > 0), so "what OSQP returns when run to
+// convergence" is the unique optimum; it is pinned by (1) two independent solvers below (OSQP-algorithm restatement at eps 1e-11
+// vs. long-double exact solver) and (2) a KKT certificate evaluated on the LITERAL 12N-variable problem -- since round 2 also on
+// the REFERENCE-built H, g, Ac, lb, ub (tests/test_gpu_ref_pin.py) -- which proves optimality independently of the method.
 //
 // Dependency-free C++17.  Literal where the reference is literal: dense rollout, dense
 // B_qp^T Q B_qp, dense constraint matrix, OSQP-style ADMM.  No closed forms, no swing elimination
@@ -990,6 +992,25 @@ int oracle_build_qp(const a1mpc_config* cfg, const a1mpc_inputs* in, int b, doub
   return 0;
 }
 
+// the intermediate members for QP `b`: mpc_states [13], mpc_states_d [13N] (A1RobotControl.cpp:452-488), A_mat_d [13x13],
+// B_mat_d_list [13N x 12], A_qp [13N x 13], B_qp [13N x 12N] (ConvexMpc.cpp:145-202), all row-major.  Any output may be NULL.
+int oracle_rollout(const a1mpc_config* cfg, const a1mpc_inputs* in, int b, double* mpc_states, double* mpc_states_d, double* A_d,
+                   double* B_d_list, double* A_qp, double* B_qp) {
+  const int N = cfg->horizon;
+  RobotState st;
+  unpack(in, b, &st);
+  ConvexMpcRestated mpc(N, cfg->q, cfg->r, cfg->mu, cfg->fz_min, cfg->fz_max);
+  std::vector<double> x0, xd;
+  drive_convex_mpc(mpc, *cfg, st, x0, xd);
+  if (mpc_states) std::memcpy(mpc_states, x0.data(), sizeof(double) * 13);
+  if (mpc_states_d) std::memcpy(mpc_states_d, xd.data(), sizeof(double) * 13 * N);
+  if (A_d) std::memcpy(A_d, mpc.A_mat_d.a.data(), sizeof(double) * 13 * 13);
+  if (B_d_list) std::memcpy(B_d_list, mpc.B_mat_d_list.a.data(), sizeof(double) * 13 * N * 12);
+  if (A_qp) std::memcpy(A_qp, mpc.A_qp.a.data(), sizeof(double) * 13 * N * 13);
+  if (B_qp) std::memcpy(B_qp, mpc.B_qp.a.data(), sizeof(double) * 13 * N * 12 * N);
+  return 0;
+}
+
 // general ConvexMpc::calculate_qp_mats with caller-supplied A_d, B_d_list (test_mpc.cpp:106-125)
 int oracle_qp_mats(const a1mpc_config* cfg, const double* A_d, const double* B_d_list, const double* x0,
                    const double* x_d, double* H, double* g) {
@@ -1211,6 +1232,34 @@ int oracle_solve_dense(const a1mpc_config* cfg, const double* H, const double* g
     if (info8) { info8[0] = oi.iter; info8[1] = oi.status; }
   }
   return 0;
+}
+
+// Generic dense QP  min 1/2 x'Px + q'x  s.t. l <= Ax <= u  through the OSQP-algorithm restatement, with the signature of the
+// solve hook of oracle/ref_shim/OsqpEigen/OsqpEigen.h (P n x n, A m x n, both COLUMN-major): this is what stands in for the absent
+// OSQP when the reference's own compute_grf / test_mpc.cpp run from oracle/_ref.  Always a cold start (x = y = 0): run to
+// eps 1e-11 the starting point does not matter, the optimum is unique (P positive definite).  y is not produced.
+static int qp_hook_common(int n, int m, const double* P, const double* q, const double* A, const double* l, const double* u,
+                          bool tight, double* x) {
+  Mat Pm(n, n), Am(m, n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) Pm(i, j) = P[(size_t)j * n + i];
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < n; ++j) Am(i, j) = A[(size_t)j * m + i];
+  OsqpSettings os;
+  if (tight) { os.eps_abs = os.eps_rel = 1e-11; os.max_iter = 400000; }
+  SparseRows As;
+  As.from_dense(Am);
+  OsqpInfo oi;
+  osqp_restated_solve(n, m, Pm, q, As, l, u, os, x, &oi);
+  return oi.status == 1 ? 0 : (tight ? 2 : 0);  // default settings may stop at max_iter like OSQP does; still "a solution"
+}
+int oracle_qp_hook_osqp_tight(int n, int m, const double* P, const double* q, const double* A, const double* l, const double* u,
+                              int /*warm*/, double* x, double* /*y*/) {
+  return qp_hook_common(n, m, P, q, A, l, u, true, x);
+}
+int oracle_qp_hook_osqp_default(int n, int m, const double* P, const double* q, const double* A, const double* l, const double* u,
+                                int /*warm*/, double* x, double* /*y*/) {
+  return qp_hook_common(n, m, P, q, A, l, u, false, x);
 }
 
 // compute_grf's QP branch (A1RobotControl.cpp:11-48, 377-445): 12 variables, 20 rows.

@@ -94,6 +94,16 @@ def build_qp(cfg, batch, b):
     return H, g, A, lb, ub
 
 
+def rollout(cfg, batch, b):
+    """mpc_states, mpc_states_d, A_d, B_d_list, A_qp, B_qp of QP b (the ConvexMpc / A1CtrlStates members compute_grf leaves)"""
+    N = cfg.horizon
+    o = dict(mpc_states=np.zeros(13), mpc_states_d=np.zeros(13 * N), A_d=np.zeros((13, 13)), B_d_list=np.zeros((13 * N, 12)),
+             A_qp=np.zeros((13 * N, 13)), B_qp=np.zeros((13 * N, 12 * N)))
+    inp = batch.c_inputs()
+    lib().oracle_rollout(C.byref(cfg), C.byref(inp), b, *[_ptr(o[k]) for k in ("mpc_states", "mpc_states_d", "A_d", "B_d_list", "A_qp", "B_qp")])
+    return o
+
+
 def qp_mats(cfg, A_d, B_d_list, x0, x_d):
     n = 12 * cfg.horizon
     H = np.zeros((n, n)); g = np.zeros(n)

@@ -7,7 +7,7 @@ extern "C" {
 int ref_leg_kinematics(const double* q, const double* rho_opt, const double* rho_fix, double* p, double* J) {
   A1Kinematics kin;
   Eigen::Vector3d qv;
-  Eigen::VectorXd ro, rf;
+  Eigen::VectorXd ro(3), rf(5);
   for (int i = 0; i < 3; ++i) { qv.data()[i] = q[i]; ro.data()[i] = rho_opt[i]; }
   for (int i = 0; i < 5; ++i) rf.data()[i] = rho_fix[i];
   Eigen::Vector3d pv = kin.fk(qv, ro, rf);

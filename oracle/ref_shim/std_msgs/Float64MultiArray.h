@@ -1,0 +1,4 @@
+// ref_shim -- TEST INFRASTRUCTURE, see ros/ros.h.
+#pragma once
+#include <vector>
+namespace std_msgs { struct Float64MultiArray { std::vector<double> data; }; }

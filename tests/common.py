@@ -27,6 +27,18 @@ def golden_groups():
     return out
 
 
+def load_ref_golden():
+    """vectors produced by the REFERENCE's own compiled sources (tests/golden/make_ref_golden.py)"""
+    with np.load(os.path.join(ROOT, "tests", "golden", "convexmpc_v1.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def ref_cfg_kwargs(G, w):
+    """keyword arguments (mass, inertia, q, r) of weight set w of the reference golden file, for O.make_config / a1mpc.default_config"""
+    v = G["w%d" % w]
+    return dict(mass=float(v[0]), inertia=tuple(v[1:10]), q=tuple(v[10:23]), r=tuple(v[23:35]))
+
+
 def obatch(O, st, sl=None):
     if sl is None:
         return O.Batch(st["x0"], st["rot"], st["foot"], st["ref"], st["contact"])
