@@ -164,24 +164,25 @@ class DeviceBatch:
     def __init__(self, eng, B, want_u=False, want_iters=True):
         self.eng, self.B = eng, B
         N = eng.cfg.horizon
-        self.x0 = eng.dalloc(12 * B * 8); self.rot = eng.dalloc(9 * B * 8); self.foot = eng.dalloc(12 * B * 8)
-        self.ref = eng.dalloc(9 * B * 8); self.contact = eng.dalloc(B * 4)
-        self.f_body = eng.dalloc(12 * B * 8); self.status = eng.dalloc(B * 4)
+        es = np.dtype(eng.ftype).itemsize
+        self.x0 = eng.dalloc(12 * B * es); self.rot = eng.dalloc(9 * B * es); self.foot = eng.dalloc(12 * B * es)
+        self.ref = eng.dalloc(9 * B * es); self.contact = eng.dalloc(B * 4)
+        self.f_body = eng.dalloc(12 * B * es); self.status = eng.dalloc(B * 4)
         self.iters = eng.dalloc(B * 4) if want_iters else None
-        self.u_full = eng.dalloc(12 * N * B * 8) if want_u else None
+        self.u_full = eng.dalloc(12 * N * B * es) if want_u else None
         self.inp = Inputs(self.x0, self.rot, self.foot, self.ref, self.contact, B)
         self.out = Outputs(self.f_body, self.status, self.iters, self.u_full, B)
 
     def upload(self, st):
         e = self.eng
         for name in ("x0", "rot", "foot", "ref", "contact"):
-            a = np.ascontiguousarray(st[name])
+            a = np.ascontiguousarray(st[name], dtype=(np.uint32 if name == "contact" else e.ftype))
             _check(lib().a1mpc_memcpy_h2d(e.h, getattr(self, name), _p(a), a.nbytes))
         e.sync()
 
     def download(self):
         e, B = self.eng, self.B
-        f = np.zeros((12, B)); status = np.zeros(B, dtype=np.int32)
+        f = np.zeros((12, B), dtype=e.ftype); status = np.zeros(B, dtype=np.int32)
         _check(lib().a1mpc_memcpy_d2h(e.h, _p(f), self.f_body, f.nbytes))
         _check(lib().a1mpc_memcpy_d2h(e.h, _p(status), self.status, status.nbytes))
         e.sync()
@@ -205,6 +206,11 @@ class Engine:
         self.h = h
         self.device = device
 
+    @property
+    def ftype(self):
+        """element type of the hot-path boundary arrays (a1mpc_config::precision)"""
+        return np.float32 if self.cfg.precision == 32 else np.float64
+
     def close(self):
         if self.h:
             lib().a1mpc_destroy(self.h)
@@ -221,9 +227,10 @@ class Engine:
         """host arrays in, host arrays out (H2D + kernels + D2H inside the call)"""
         B = st["x0"].shape[1]
         N = self.cfg.horizon
-        a = {k: np.ascontiguousarray(st[k], dtype=(np.uint32 if k == "contact" else np.float64)) for k in ("x0", "rot", "foot", "ref", "contact")}
-        f = np.zeros((12, B)); status = np.zeros(B, dtype=np.int32); iters = np.zeros(B, dtype=np.int32)
-        u = np.zeros((12 * N, B)) if want_u else None
+        ft = self.ftype     # float32 arrays at the boundary when cfg.precision == 32
+        a = {k: np.ascontiguousarray(st[k], dtype=(np.uint32 if k == "contact" else ft)) for k in ("x0", "rot", "foot", "ref", "contact")}
+        f = np.zeros((12, B), dtype=ft); status = np.zeros(B, dtype=np.int32); iters = np.zeros(B, dtype=np.int32)
+        u = np.zeros((12 * N, B), dtype=ft) if want_u else None
         inp = Inputs(_p(a["x0"]), _p(a["rot"]), _p(a["foot"]), _p(a["ref"]), _p(a["contact"]), B)
         out = Outputs(_p(f), _p(status), _p(iters), _p(u), B)
         _check(lib().a1mpc_solve_batch(self.h, B, C.byref(inp), C.byref(out)))
@@ -239,8 +246,8 @@ class Engine:
     def solve_warm(self, st, warm, shift=0):
         """a1mpc_solve_batch_warm: host arrays in/out, `warm` from warm_alloc (updated in place on the device)"""
         B = st["x0"].shape[1]
-        a = {k: np.ascontiguousarray(st[k], dtype=(np.uint32 if k == "contact" else np.float64)) for k in ("x0", "rot", "foot", "ref", "contact")}
-        f = np.zeros((12, B)); status = np.zeros(B, dtype=np.int32); iters = np.zeros(B, dtype=np.int32)
+        a = {k: np.ascontiguousarray(st[k], dtype=(np.uint32 if k == "contact" else self.ftype)) for k in ("x0", "rot", "foot", "ref", "contact")}
+        f = np.zeros((12, B), dtype=self.ftype); status = np.zeros(B, dtype=np.int32); iters = np.zeros(B, dtype=np.int32)
         inp = Inputs(_p(a["x0"]), _p(a["rot"]), _p(a["foot"]), _p(a["ref"]), _p(a["contact"]), B)
         out = Outputs(_p(f), _p(status), _p(iters), None, B)
         _check(lib().a1mpc_solve_batch_warm(self.h, B, C.byref(inp), C.byref(out), warm, int(shift)))
@@ -250,11 +257,12 @@ class Engine:
         """BASELINE config 4 (extension): per-step contact schedule [N,B] and/or terrain normals [12,B]"""
         B = st["x0"].shape[1]
         N = self.cfg.horizon
-        a = {k: np.ascontiguousarray(st[k], dtype=(np.uint32 if k == "contact" else np.float64)) for k in ("x0", "rot", "foot", "ref", "contact")}
+        ft = self.ftype
+        a = {k: np.ascontiguousarray(st[k], dtype=(np.uint32 if k == "contact" else ft)) for k in ("x0", "rot", "foot", "ref", "contact")}
         sc = np.ascontiguousarray(sched, dtype=np.uint32) if sched is not None else None
-        nm = np.ascontiguousarray(normals, dtype=np.float64) if normals is not None else None
-        f = np.zeros((12, B)); status = np.zeros(B, dtype=np.int32); iters = np.zeros(B, dtype=np.int32)
-        u = np.zeros((12 * N, B)) if want_u else None
+        nm = np.ascontiguousarray(normals, dtype=ft) if normals is not None else None
+        f = np.zeros((12, B), dtype=ft); status = np.zeros(B, dtype=np.int32); iters = np.zeros(B, dtype=np.int32)
+        u = np.zeros((12 * N, B), dtype=ft) if want_u else None
         inp = Inputs(_p(a["x0"]), _p(a["rot"]), _p(a["foot"]), _p(a["ref"]), _p(a["contact"]), B)
         ext = InputsExt(_p(sc), _p(nm))
         out = Outputs(_p(f), _p(status), _p(iters), _p(u), B)

@@ -29,6 +29,8 @@ int fail(int code, const std::string& msg) {
 
 }  // namespace
 
+extern "C" void a1mpc_internal_nccl_destroy(void* comm);   // a1mpc_nccl.cpp
+
 struct a1mpc_handle {
   int device = 0;
   int sm_count = 0;
@@ -39,7 +41,7 @@ struct a1mpc_handle {
   DevParams P;
   a1mpc::ClassLaunch cls[5];  // index = number of stance feet
   a1mpc::ClassLaunch cls_ext;  // extended path (config 4)
-  a1mpc::ClassLaunch cls_sched2;   // its compacted two-feet-per-step class (opt-in: A1MPC_EXT_COMPACT=1)
+  a1mpc::ClassLaunch cls_sched2;   // its compacted two-feet-per-step class (N = 10; A1MPC_EXT_COMPACT=0 disables it)
   bool ext_compact = false;
   double* d_rec_ext = nullptr;
   size_t cap_ext = 0;
@@ -212,7 +214,7 @@ int a1mpc_create(a1mpc_handle** out, const a1mpc_config* cfg, int device) {
   if (!out || !cfg) return fail(A1MPC_EINVAL, "null argument");
   *out = nullptr;
   if (cfg->horizon != 10 && cfg->horizon != 20) return fail(A1MPC_EINVAL, "horizon must be 10 or 20");
-  if (cfg->precision != 64) return fail(A1MPC_EINVAL, "precision must be 64 (fp32 is not implemented; see DESIGN.md)");
+  if (cfg->precision != 64 && cfg->precision != 32) return fail(A1MPC_EINVAL, "precision must be 64 or 32 (see include/a1mpc.h)");
   if (!(cfg->fz_min == 0.0)) return fail(A1MPC_EINVAL, "fz_min must be 0 (the reference hard-codes it, ConvexMpc.cpp:223)");
   if (!(cfg->mu > 0.0) || !(cfg->fz_max > 0.0) || !(cfg->mass > 0.0) || !(cfg->dt > 0.0)) return fail(A1MPC_EINVAL, "mu, fz_max, mass, dt must be positive");
   for (int i = 0; i < 12; ++i)
@@ -259,9 +261,10 @@ int a1mpc_create(a1mpc_handle** out, const a1mpc_config* cfg, int device) {
     if (e != cudaSuccess) return bail(fail(A1MPC_ECUDA, std::string("kernel setup: ") + cudaGetErrorString(e)));
     e = ext_setup(cfg->horizon, h->sm_count, h->cls_ext);
     if (e != cudaSuccess) return bail(fail(A1MPC_ECUDA, std::string("ext kernel setup: ") + cudaGetErrorString(e)));
-    {   // experimental this round (emulator-validated only): schedules with two stance feet per step on the compact direct kernel
+    {   // schedules with two stance feet in every step run on the compact direct kernel (a1mpc_sched.cuh): 2.5 M instead of 1.5 M
+        // QPs/s end to end on a B200 at B = 16384 (profiles/r02a_call1_*.txt).  A1MPC_EXT_COMPACT=0 keeps everything on the general kernel (A/B).
       const char* ev = std::getenv("A1MPC_EXT_COMPACT");
-      if (ev && ev[0] == '1' && cfg->horizon == 10) {
+      if (!(ev && ev[0] == '0') && cfg->horizon == 10) {
         e = sched2_setup(h->sm_count, h->cls_sched2);
         if (e != cudaSuccess) return bail(fail(A1MPC_ECUDA, std::string("compact ext kernel setup: ") + cudaGetErrorString(e)));
         h->ext_compact = true;
@@ -279,6 +282,8 @@ int a1mpc_destroy(a1mpc_handle* h) {
   if (!h) return A1MPC_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->gather_stream) cudaStreamSynchronize(h->gather_stream);
+  if (h->nccl_comm) { a1mpc_internal_nccl_destroy(h->nccl_comm); h->nccl_comm = nullptr; }   // before its streams go away
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(h->d_rec); fr(h->d_count); fr(h->d_x0); fr(h->d_rot); fr(h->d_foot); fr(h->d_ref); fr(h->d_f); fr(h->d_u);
   fr(h->d_contact); fr(h->d_status); fr(h->d_iters); fr(h->d_side); fr(h->d_flush); fr(h->d_lists);
@@ -301,31 +306,36 @@ static int solve_batch_impl(a1mpc_handle* h, int B, const a1mpc_inputs* in, cons
   if (!in->x0 || !in->rot || !in->foot || !in->ref || !in->contact || !out->f_body || !out->status) return fail(A1MPC_EINVAL, "null input/output array");
   if (in->ld < (size_t)B || out->ld < (size_t)B) return fail(A1MPC_EINVAL, "ld < B");
   CK(cudaSetDevice(h->device));
+  // every array of the call lives on the same side (a host pointer dereferenced by a kernel is a sticky fault for the whole context)
   const bool dev_in = is_device_ptr(in->x0), dev_out = is_device_ptr(out->f_body);
-  if (dev_in != dev_out || dev_in != is_device_ptr(in->contact) || dev_in != is_device_ptr(out->status))
-    return fail(A1MPC_EINVAL, "inputs and outputs must be all-host or all-device");
+  const void* all_ptrs[] = {in->rot, in->foot, in->ref, in->contact, out->status, out->iters, out->u_full};
+  bool mixed = (dev_in != dev_out);
+  for (const void* q : all_ptrs) mixed = mixed || (q && is_device_ptr(q) != dev_in);
+  if (mixed) return fail(A1MPC_EINVAL, "inputs and outputs must be all-host or all-device");
+  const int f32 = (h->cfg.precision == 32) ? 1 : 0;   // fp32 arrays at the boundary, fp64 inside
+  const size_t es = f32 ? 4 : 8;
   int rc;
   if (dev_in) {
     if ((rc = ensure_capacity(h, B, false, false))) return rc;
-    DevInputs di{in->x0, in->rot, in->foot, in->ref, in->contact, in->ld};
-    DevOutputs dout{out->f_body, out->status, out->iters, out->u_full, out->ld};
+    DevInputs di{in->x0, in->rot, in->foot, in->ref, in->contact, in->ld, f32};
+    DevOutputs dout{out->f_body, out->status, out->iters, out->u_full, out->ld, f32};
     return enqueue_solve(h, B, di, dout, warm, shift);
   }
   if ((rc = ensure_capacity(h, B, true, out->u_full != nullptr))) return rc;
   const size_t Bs = (size_t)B;
-  if ((rc = copy_rows(h->stream, h->d_x0, Bs, in->x0, in->ld, 12, Bs, 8, cudaMemcpyHostToDevice))) return rc;
-  if ((rc = copy_rows(h->stream, h->d_rot, Bs, in->rot, in->ld, 9, Bs, 8, cudaMemcpyHostToDevice))) return rc;
-  if ((rc = copy_rows(h->stream, h->d_foot, Bs, in->foot, in->ld, 12, Bs, 8, cudaMemcpyHostToDevice))) return rc;
-  if ((rc = copy_rows(h->stream, h->d_ref, Bs, in->ref, in->ld, 9, Bs, 8, cudaMemcpyHostToDevice))) return rc;
+  if ((rc = copy_rows(h->stream, h->d_x0, Bs, in->x0, in->ld, 12, Bs, es, cudaMemcpyHostToDevice))) return rc;
+  if ((rc = copy_rows(h->stream, h->d_rot, Bs, in->rot, in->ld, 9, Bs, es, cudaMemcpyHostToDevice))) return rc;
+  if ((rc = copy_rows(h->stream, h->d_foot, Bs, in->foot, in->ld, 12, Bs, es, cudaMemcpyHostToDevice))) return rc;
+  if ((rc = copy_rows(h->stream, h->d_ref, Bs, in->ref, in->ld, 9, Bs, es, cudaMemcpyHostToDevice))) return rc;
   CK(cudaMemcpyAsync(h->d_contact, in->contact, Bs * 4, cudaMemcpyHostToDevice, h->stream));
-  DevInputs di{h->d_x0, h->d_rot, h->d_foot, h->d_ref, h->d_contact, Bs};
-  DevOutputs dout{h->d_f, h->d_status, out->iters ? h->d_iters : nullptr, out->u_full ? h->d_u : nullptr, Bs};
+  DevInputs di{h->d_x0, h->d_rot, h->d_foot, h->d_ref, h->d_contact, Bs, f32};
+  DevOutputs dout{h->d_f, h->d_status, out->iters ? h->d_iters : nullptr, out->u_full ? h->d_u : nullptr, Bs, f32};
   if ((rc = enqueue_solve(h, B, di, dout, warm, shift))) return rc;
-  if ((rc = copy_rows(h->stream, out->f_body, out->ld, h->d_f, Bs, 12, Bs, 8, cudaMemcpyDeviceToHost))) return rc;
+  if ((rc = copy_rows(h->stream, out->f_body, out->ld, h->d_f, Bs, 12, Bs, es, cudaMemcpyDeviceToHost))) return rc;
   CK(cudaMemcpyAsync(out->status, h->d_status, Bs * 4, cudaMemcpyDeviceToHost, h->stream));
   if (out->iters) CK(cudaMemcpyAsync(out->iters, h->d_iters, Bs * 4, cudaMemcpyDeviceToHost, h->stream));
   if (out->u_full)
-    if ((rc = copy_rows(h->stream, out->u_full, out->ld, h->d_u, Bs, 12 * h->cfg.horizon, Bs, 8, cudaMemcpyDeviceToHost))) return rc;
+    if ((rc = copy_rows(h->stream, out->u_full, out->ld, h->d_u, Bs, 12 * h->cfg.horizon, Bs, es, cudaMemcpyDeviceToHost))) return rc;
   CK(cudaStreamSynchronize(h->stream));
   return A1MPC_OK;
 }
@@ -368,8 +378,13 @@ int a1mpc_solve_batch_ext(a1mpc_handle* h, int B, const a1mpc_inputs* in, const 
   const int N = h->cfg.horizon;
   const size_t Bs = (size_t)B;
   const bool dev = is_device_ptr(in->x0);
-  if (dev != is_device_ptr(out->f_body) || (ext->contact_sched && dev != is_device_ptr(ext->contact_sched)) || (ext->normals && dev != is_device_ptr(ext->normals)))
-    return fail(A1MPC_EINVAL, "inputs and outputs must be all-host or all-device");
+  {
+    const void* all_ptrs[] = {in->rot, in->foot, in->ref, in->contact, out->f_body, out->status, out->iters, out->u_full, ext->contact_sched, ext->normals};
+    for (const void* q : all_ptrs)
+      if (q && is_device_ptr(q) != dev) return fail(A1MPC_EINVAL, "inputs and outputs must be all-host or all-device");
+  }
+  const int f32 = (h->cfg.precision == 32) ? 1 : 0;
+  const size_t es = f32 ? 4 : 8;
   int rc;
   if ((rc = ensure_capacity(h, B, !dev, !dev && out->u_full != nullptr))) return rc;
   if (Bs > h->cap_ext) {
@@ -379,8 +394,8 @@ int a1mpc_solve_batch_ext(a1mpc_handle* h, int B, const a1mpc_inputs* in, const 
     CK(cudaMalloc(&h->d_rec_ext, 2 * h->cap * REC_EXT_BYTES));   // second half: queue of the compacted class
     h->cap_ext = h->cap;
   }
-  DevInputs di{in->x0, in->rot, in->foot, in->ref, in->contact, in->ld};
-  DevOutputs dout{out->f_body, out->status, out->iters, out->u_full, out->ld};
+  DevInputs di{in->x0, in->rot, in->foot, in->ref, in->contact, in->ld, f32};
+  DevOutputs dout{out->f_body, out->status, out->iters, out->u_full, out->ld, f32};
   const uint32_t* dsched = ext->contact_sched;
   const double* dnorm = ext->normals;
   if (!dev) {
@@ -393,21 +408,21 @@ int a1mpc_solve_batch_ext(a1mpc_handle* h, int B, const a1mpc_inputs* in, const 
       CK(cudaMalloc(&h->d_normals, 12 * h->cap * 8));
       h->cap_ext_mirror = h->cap;
     }
-    if ((rc = copy_rows(h->stream, h->d_x0, Bs, in->x0, in->ld, 12, Bs, 8, cudaMemcpyHostToDevice))) return rc;
-    if ((rc = copy_rows(h->stream, h->d_rot, Bs, in->rot, in->ld, 9, Bs, 8, cudaMemcpyHostToDevice))) return rc;
-    if ((rc = copy_rows(h->stream, h->d_foot, Bs, in->foot, in->ld, 12, Bs, 8, cudaMemcpyHostToDevice))) return rc;
-    if ((rc = copy_rows(h->stream, h->d_ref, Bs, in->ref, in->ld, 9, Bs, 8, cudaMemcpyHostToDevice))) return rc;
+    if ((rc = copy_rows(h->stream, h->d_x0, Bs, in->x0, in->ld, 12, Bs, es, cudaMemcpyHostToDevice))) return rc;
+    if ((rc = copy_rows(h->stream, h->d_rot, Bs, in->rot, in->ld, 9, Bs, es, cudaMemcpyHostToDevice))) return rc;
+    if ((rc = copy_rows(h->stream, h->d_foot, Bs, in->foot, in->ld, 12, Bs, es, cudaMemcpyHostToDevice))) return rc;
+    if ((rc = copy_rows(h->stream, h->d_ref, Bs, in->ref, in->ld, 9, Bs, es, cudaMemcpyHostToDevice))) return rc;
     CK(cudaMemcpyAsync(h->d_contact, in->contact, Bs * 4, cudaMemcpyHostToDevice, h->stream));
     if (ext->contact_sched) {
       if ((rc = copy_rows(h->stream, h->d_sched, Bs, ext->contact_sched, in->ld, N, Bs, 4, cudaMemcpyHostToDevice))) return rc;
       dsched = h->d_sched;
     }
     if (ext->normals) {
-      if ((rc = copy_rows(h->stream, h->d_normals, Bs, ext->normals, in->ld, 12, Bs, 8, cudaMemcpyHostToDevice))) return rc;
+      if ((rc = copy_rows(h->stream, h->d_normals, Bs, ext->normals, in->ld, 12, Bs, es, cudaMemcpyHostToDevice))) return rc;
       dnorm = h->d_normals;
     }
-    di = DevInputs{h->d_x0, h->d_rot, h->d_foot, h->d_ref, h->d_contact, Bs};
-    dout = DevOutputs{h->d_f, h->d_status, out->iters ? h->d_iters : nullptr, out->u_full ? h->d_u : nullptr, Bs};
+    di = DevInputs{h->d_x0, h->d_rot, h->d_foot, h->d_ref, h->d_contact, Bs, f32};
+    dout = DevOutputs{h->d_f, h->d_status, out->iters ? h->d_iters : nullptr, out->u_full ? h->d_u : nullptr, Bs, f32};
   }
   CK(cudaMemsetAsync(h->d_count, 0, 8 * sizeof(int), h->stream));
   if (h->ext_compact && dsched) {
@@ -422,11 +437,11 @@ int a1mpc_solve_batch_ext(a1mpc_handle* h, int B, const a1mpc_inputs* in, const 
   }
   CK(cudaGetLastError());
   if (!dev) {
-    if ((rc = copy_rows(h->stream, out->f_body, out->ld, h->d_f, Bs, 12, Bs, 8, cudaMemcpyDeviceToHost))) return rc;
+    if ((rc = copy_rows(h->stream, out->f_body, out->ld, h->d_f, Bs, 12, Bs, es, cudaMemcpyDeviceToHost))) return rc;
     CK(cudaMemcpyAsync(out->status, h->d_status, Bs * 4, cudaMemcpyDeviceToHost, h->stream));
     if (out->iters) CK(cudaMemcpyAsync(out->iters, h->d_iters, Bs * 4, cudaMemcpyDeviceToHost, h->stream));
     if (out->u_full)
-      if ((rc = copy_rows(h->stream, out->u_full, out->ld, h->d_u, Bs, 12 * N, Bs, 8, cudaMemcpyDeviceToHost))) return rc;
+      if ((rc = copy_rows(h->stream, out->u_full, out->ld, h->d_u, Bs, 12 * N, Bs, es, cudaMemcpyDeviceToHost))) return rc;
     CK(cudaStreamSynchronize(h->stream));
   }
   return A1MPC_OK;

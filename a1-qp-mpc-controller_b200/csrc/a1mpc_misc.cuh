@@ -15,23 +15,23 @@ __global__ void pack_kernel(DevInputs in, int B, double* __restrict__ rec, int c
   const uint32_t mask = in.contact[b] & 15u;
   const int ns = __popc(mask);
   if (ns == 0) {  // every foot is pinned to zero by fz in [0,0] (ConvexMpc.cpp:233,238)
-    for (int k = 0; k < 12; ++k) out.f_body[(size_t)k * out.ld + b] = 0.0;
+    for (int k = 0; k < 12; ++k) st_out(out.f_body, (size_t)k * out.ld + b, 0.0, out.f32);
     out.status[b] = A1MPC_STATUS_NO_CONTACT;
     if (out.iters) out.iters[b] = 0;
     if (out.u_full)
-      for (int k = 0; k < 12 * horizon; ++k) out.u_full[(size_t)k * out.ld + b] = 0.0;
+      for (int k = 0; k < 12 * horizon; ++k) st_out(out.u_full, (size_t)k * out.ld + b, 0.0, out.f32);
     return;
   }
   const int slot = atomicAdd(&count[ns], 1);
   double* r = rec + ((size_t)(ns - 1) * cap + slot) * REC_DOUBLES;
 #pragma unroll
-  for (int k = 0; k < 12; ++k) r[k] = in.x0[(size_t)k * in.ld + b];
+  for (int k = 0; k < 12; ++k) r[k] = ld_in(in.x0, (size_t)k * in.ld + b, in.f32);
 #pragma unroll
-  for (int k = 0; k < 9; ++k) r[12 + k] = in.rot[(size_t)k * in.ld + b];
+  for (int k = 0; k < 9; ++k) r[12 + k] = ld_in(in.rot, (size_t)k * in.ld + b, in.f32);
 #pragma unroll
-  for (int k = 0; k < 12; ++k) r[21 + k] = in.foot[(size_t)k * in.ld + b];
+  for (int k = 0; k < 12; ++k) r[21 + k] = ld_in(in.foot, (size_t)k * in.ld + b, in.f32);
 #pragma unroll
-  for (int k = 0; k < 9; ++k) r[33 + k] = in.ref[(size_t)k * in.ld + b];
+  for (int k = 0; k < 9; ++k) r[33 + k] = ld_in(in.ref, (size_t)k * in.ld + b, in.f32);
   r[42] = __hiloint2double((int)mask, b);
   r[43] = 0.0;
 }
@@ -48,23 +48,23 @@ __global__ void pack_ext_kernel(DevInputs in, const uint32_t* __restrict__ sched
     else s1 |= m << (4 * (st - 16));
   }
   if (s0 == 0ull && s1 == 0ull) {
-    for (int k = 0; k < 12; ++k) out.f_body[(size_t)k * out.ld + b] = 0.0;
+    for (int k = 0; k < 12; ++k) st_out(out.f_body, (size_t)k * out.ld + b, 0.0, out.f32);
     out.status[b] = A1MPC_STATUS_NO_CONTACT;
     if (out.iters) out.iters[b] = 0;
     if (out.u_full)
-      for (int k = 0; k < 12 * horizon; ++k) out.u_full[(size_t)k * out.ld + b] = 0.0;
+      for (int k = 0; k < 12 * horizon; ++k) st_out(out.u_full, (size_t)k * out.ld + b, 0.0, out.f32);
     return;
   }
   const int slot = atomicAdd(&count[5], 1);
   double* r = rec + (size_t)slot * REC_EXT_DOUBLES;
 #pragma unroll
-  for (int k = 0; k < 12; ++k) r[k] = in.x0[(size_t)k * in.ld + b];
+  for (int k = 0; k < 12; ++k) r[k] = ld_in(in.x0, (size_t)k * in.ld + b, in.f32);
 #pragma unroll
-  for (int k = 0; k < 9; ++k) r[12 + k] = in.rot[(size_t)k * in.ld + b];
+  for (int k = 0; k < 9; ++k) r[12 + k] = ld_in(in.rot, (size_t)k * in.ld + b, in.f32);
 #pragma unroll
-  for (int k = 0; k < 12; ++k) r[21 + k] = in.foot[(size_t)k * in.ld + b];
+  for (int k = 0; k < 12; ++k) r[21 + k] = ld_in(in.foot, (size_t)k * in.ld + b, in.f32);
 #pragma unroll
-  for (int k = 0; k < 9; ++k) r[33 + k] = in.ref[(size_t)k * in.ld + b];
+  for (int k = 0; k < 9; ++k) r[33 + k] = ld_in(in.ref, (size_t)k * in.ld + b, in.f32);
   r[42] = __hiloint2double((int)(s0 & 15ull), b);
   r[43] = 0.0;
   r[44] = __longlong_as_double((long long)s0);
@@ -72,7 +72,7 @@ __global__ void pack_ext_kernel(DevInputs in, const uint32_t* __restrict__ sched
   for (int leg = 0; leg < 4; ++leg) {
     double nx = 0.0, ny = 0.0, nz = 1.0;
     if (normals) {
-      nx = normals[(size_t)(3 * leg) * in.ld + b]; ny = normals[(size_t)(3 * leg + 1) * in.ld + b]; nz = normals[(size_t)(3 * leg + 2) * in.ld + b];
+      nx = ld_in(normals, (size_t)(3 * leg) * in.ld + b, in.f32); ny = ld_in(normals, (size_t)(3 * leg + 1) * in.ld + b, in.f32); nz = ld_in(normals, (size_t)(3 * leg + 2) * in.ld + b, in.f32);
       const double inv = rsqrt(nx * nx + ny * ny + nz * nz);
       nx *= inv; ny *= inv; nz *= inv;
     }
@@ -95,23 +95,23 @@ __global__ void pack_ext2_kernel(DevInputs in, const uint32_t* __restrict__ sche
     else s1 |= m << (4 * (st - 16));
   }
   if (s0 == 0ull && s1 == 0ull) {
-    for (int k = 0; k < 12; ++k) out.f_body[(size_t)k * out.ld + b] = 0.0;
+    for (int k = 0; k < 12; ++k) st_out(out.f_body, (size_t)k * out.ld + b, 0.0, out.f32);
     out.status[b] = A1MPC_STATUS_NO_CONTACT;
     if (out.iters) out.iters[b] = 0;
     if (out.u_full)
-      for (int k = 0; k < 12 * horizon; ++k) out.u_full[(size_t)k * out.ld + b] = 0.0;
+      for (int k = 0; k < 12 * horizon; ++k) st_out(out.u_full, (size_t)k * out.ld + b, 0.0, out.f32);
     return;
   }
   const int slot = atomicAdd(&count[two ? 6 : 5], 1);
   double* r = rec + ((two ? (size_t)cap : (size_t)0) + (size_t)slot) * REC_EXT_DOUBLES;
 #pragma unroll
-  for (int k = 0; k < 12; ++k) r[k] = in.x0[(size_t)k * in.ld + b];
+  for (int k = 0; k < 12; ++k) r[k] = ld_in(in.x0, (size_t)k * in.ld + b, in.f32);
 #pragma unroll
-  for (int k = 0; k < 9; ++k) r[12 + k] = in.rot[(size_t)k * in.ld + b];
+  for (int k = 0; k < 9; ++k) r[12 + k] = ld_in(in.rot, (size_t)k * in.ld + b, in.f32);
 #pragma unroll
-  for (int k = 0; k < 12; ++k) r[21 + k] = in.foot[(size_t)k * in.ld + b];
+  for (int k = 0; k < 12; ++k) r[21 + k] = ld_in(in.foot, (size_t)k * in.ld + b, in.f32);
 #pragma unroll
-  for (int k = 0; k < 9; ++k) r[33 + k] = in.ref[(size_t)k * in.ld + b];
+  for (int k = 0; k < 9; ++k) r[33 + k] = ld_in(in.ref, (size_t)k * in.ld + b, in.f32);
   r[42] = __hiloint2double((int)(s0 & 15ull), b);
   r[43] = 0.0;
   r[44] = __longlong_as_double((long long)s0);
@@ -119,7 +119,7 @@ __global__ void pack_ext2_kernel(DevInputs in, const uint32_t* __restrict__ sche
   for (int leg = 0; leg < 4; ++leg) {
     double nx = 0.0, ny = 0.0, nz = 1.0;
     if (normals) {
-      nx = normals[(size_t)(3 * leg) * in.ld + b]; ny = normals[(size_t)(3 * leg + 1) * in.ld + b]; nz = normals[(size_t)(3 * leg + 2) * in.ld + b];
+      nx = ld_in(normals, (size_t)(3 * leg) * in.ld + b, in.f32); ny = ld_in(normals, (size_t)(3 * leg + 1) * in.ld + b, in.f32); nz = ld_in(normals, (size_t)(3 * leg + 2) * in.ld + b, in.f32);
       const double inv = rsqrt(nx * nx + ny * ny + nz * nz);
       nx *= inv; ny *= inv; nz *= inv;
     }
@@ -133,11 +133,11 @@ __global__ void unsupported_kernel(const double* __restrict__ rec, const int* __
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= count[cls]) return;
   const int b = __double2loint(rec[(size_t)q * REC_DOUBLES + 42]);
-  for (int k = 0; k < 12; ++k) out.f_body[(size_t)k * out.ld + b] = 0.0;
+  for (int k = 0; k < 12; ++k) st_out(out.f_body, (size_t)k * out.ld + b, 0.0, out.f32);
   out.status[b] = A1MPC_STATUS_NUMERICAL;
   if (out.iters) out.iters[b] = 0;
   if (out.u_full)
-    for (int k = 0; k < 12 * horizon; ++k) out.u_full[(size_t)k * out.ld + b] = 0.0;
+    for (int k = 0; k < 12 * horizon; ++k) st_out(out.u_full, (size_t)k * out.ld + b, 0.0, out.f32);
 }
 
 // compute_joint_torques (A1RobotControl.cpp:289-319): thread per QP, every access batch-major coalesced.  HBM bound:

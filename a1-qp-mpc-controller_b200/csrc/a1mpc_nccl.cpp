@@ -83,6 +83,11 @@ int a1mpc_nccl_init(a1mpc_handle* h, int nranks, int rank, const void* unique_id
   return A1MPC_OK;
 }
 
+// a1mpc_destroy: release the communicator (peers blocked in their own destroy otherwise wait for it)
+void a1mpc_internal_nccl_destroy(void* comm) {
+  if (comm && g.destroy) g.destroy(comm);
+}
+
 int a1mpc_allgather_forces(a1mpc_handle* h, const double* f_local, double* f_all, int B_local) {
   if (!h || !f_local || !f_all || B_local <= 0) return A1MPC_EINVAL;
   void* comm = *a1mpc_internal_nccl_slot(h);

@@ -142,7 +142,10 @@ __global__ void __launch_bounds__(32 * WPC) solve_kernel_sched2(const __grid_con
   if (A1MPC_RV && WPC > 1 && threadIdx.x == 0) mbar_init(smem + 2 * N * N, WPC);
   __syncthreads();
   const int nq = count[6];
-  const int gw = blockIdx.x * WPC + wib, nw = gridDim.x * WPC;
+  // QP q -> warp (q / gridDim.x) of CTA (q % gridDim.x): a class with fewer QPs than the grid has CTAs runs ONE warp per SM
+  // (its neighbours find no work and leave the rendezvous at once), so that at B ~ 1000 the slowest QP -- which is the step --
+  // has an SM's issue slots and instruction cache to itself; with full grids every warp is busy either way
+  const int gw = wib * gridDim.x + blockIdx.x, nw = gridDim.x * WPC;
   uint32_t parity = 0;
 #pragma unroll 1
   for (int q = gw; q < nq; q += nw) {
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(32 * WPC) solve_kernel_sched2(const __grid_con
         for (int a = 0; a < 3; ++a) f[a] = c.rec[12 + a] * wx_ + c.rec[15 + a] * wy_ + c.rec[18 + a] * wz_;
       }
 #pragma unroll
-      for (int a = 0; a < 3; ++a) out.f_body[(size_t)(3 * lane + a) * out.ld + b] = f[a];
+      for (int a = 0; a < 3; ++a) st_out(out.f_body, (size_t)(3 * lane + a) * out.ld + b, f[a], out.f32);
     }
     if (lane == 0) {
       out.status[b] = status;
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(32 * WPC) solve_kernel_sched2(const __grid_con
           for (int bb = 0; bb < 3; ++bb) { terrain_col(c.rec + 46 + 3 * leg, bb, col); acc = fma(col[a], c.vy[3 * k + bb], acc); }
           v = acc * FSCALE;
         }
-        out.u_full[(size_t)e * out.ld + b] = v;
+        st_out(out.u_full, (size_t)e * out.ld + b, v, out.f32);
       }
     }
     __syncwarp();

@@ -27,7 +27,7 @@ static cudaError_t setup_one_warm(const ClassLaunch& c) {
 template <int NS, int N, int WPC, int LSM>
 static void launch_one_warm(const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count,
                             const DevOutputs& out, uint32_t* warm, int shift) {
-  int grid = (B + WPC - 1) / WPC;
+  int grid = B;   // one QP per CTA first (see the q -> warp map in a1mpc_solve_body.inc), at most the persistent grid
   if (grid > c.max_ctas) grid = c.max_ctas;
   if (grid < 1) grid = 1;
   solve_kernel_warm<NS, N, WPC, LSM><<<grid, 32 * WPC, c.smem, st>>>(P, rec, count, out, warm, shift);
@@ -35,7 +35,7 @@ static void launch_one_warm(const ClassLaunch& c, cudaStream_t st, int B, const 
 
 template <int NS, int N, int WPC, int LSM>
 static void launch_one(const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count, const DevOutputs& out) {
-  int grid = (B + WPC - 1) / WPC;
+  int grid = B;   // one QP per CTA first (see the q -> warp map in a1mpc_solve_body.inc), at most the persistent grid
   if (grid > c.max_ctas) grid = c.max_ctas;
   if (grid < 1) grid = 1;
   solve_kernel<NS, N, WPC, LSM><<<grid, 32 * WPC, c.smem, st>>>(P, rec, count, out);

@@ -58,10 +58,21 @@ typedef struct a1mpc_handle a1mpc_handle;
  *   q[13], r[12]     q_weights, r_weights (un-doubled; the engine applies the factor 2 of
  *                    ConvexMpc.cpp:20,41)
  *   max_iter, tol    solver controls; 0 selects the defaults (40, 1e-9 switch-over mu)
+ *   precision        64: every array of the boundary is fp64 (the reference's arithmetic type).
+ *                    32: BASELINE config 3's "fp32" -- the floating-point arrays of the HOT-PATH boundary (a1mpc_solve_batch,
+ *                        a1mpc_solve_batch_warm, a1mpc_solve_batch_ext: x0, rot, foot, ref, normals in; f_body, u_full out) hold
+ *                        float instead of double, 224 instead of 440 bytes per QP; they are declared `double*` below and
+ *                        reinterpreted.  The arithmetic in between stays fp64 with the in-kernel KKT certificate: the reduced
+ *                        systems have condition numbers of 1e5 (N=10) .. 1e6 (N=20), an fp32 factorisation cannot certify
+ *                        1e-4 N, and the only fp32-input tensor-core MMA (tf32, 10-bit mantissa) breaks down on 85 % of the
+ *                        QPs (profiles/r01_notes.md).  Accuracy contract: the returned forces are the exact optimum of the QP
+ *                        posed by the fp32-rounded inputs, rounded to fp32 -- |f - f*(rounded inputs)| <= 1e-4 N + 1 fp32 ulp.
+ *                        The parity / neighbouring entry points (build_qp, qp_mats, solve_dense, grf_qp, torques, plan,
+ *                        kinematics, EKF) are fp64 whatever this field says.
  */
 typedef struct a1mpc_config {
   int    horizon;
-  int    precision;      /* 64 (fp64 everywhere).  32 is reserved  */
+  int    precision;      /* 64 | 32 (fp32 arrays at the hot-path boundary, see above)  */
   double dt;
   double mu, fz_min, fz_max;
   double mass;
@@ -115,8 +126,10 @@ int  a1mpc_device_count(void);
 
 /* ---- the hot path: replaces compute_grf's MPC branch for B robots -------------------------- */
 /* One call = build (linearise, condense, Hessian, gradient) + QP solve + force extraction for
- * every QP of the batch.  Host pointers: pinned-staged H2D, solve, D2H, synchronous.  Device
- * pointers: enqueued on the handle's stream, asynchronous (use a1mpc_sync). */
+ * every QP of the batch.  Host pointers: cudaMemcpy2DAsync straight from / to the caller's arrays (pinned memory from
+ * a1mpc_host_alloc makes them truly asynchronous DMA; pageable memory works and is staged by the driver), solve, D2H,
+ * then one stream synchronise: the call is synchronous.  Device pointers: enqueued on the handle's stream, asynchronous
+ * (use a1mpc_sync).  ALL arrays of one call must live on the same side (checked: A1MPC_EINVAL on a mix). */
 int  a1mpc_solve_batch(a1mpc_handle* h, int B, const a1mpc_inputs* in, const a1mpc_outputs* out);
 
 /* ---- device-resident warm start across control ticks --------------------------------------------------
@@ -186,7 +199,8 @@ int  a1mpc_grf_qp_batch(a1mpc_handle* h, int B, const double* root_acc, const do
  *   f_kin   [12][B]  foot_forces_kin, leg-major (swing-leg PD force, A1RobotControl.cpp:286)
  *   jac     [36][B]  the four 3x3 diagonal blocks of j_foot, leg-major then row-major (A1CtrlStates.h:409)
  *   contact [B]      bit i = contacts[i]
- *   km_foot[3], torques_gravity[12]: batch-uniform (A1CtrlStates.h:122,129)
+ *   km_foot[3], torques_gravity[12]: batch-uniform (A1CtrlStates.h:122,129), ALWAYS HOST arrays (read by the call itself, also when
+ *                    the batch arrays are device pointers)
  *   tau     [12][B]  in/out: stance legs  J^T (-f_grf),  swing legs  J^-1 (km_foot .* f_kin)  (partial-pivot LU),
  *                    + torques_gravity; an entry whose result is NaN keeps its previous value (:314-317). */
 int  a1mpc_joint_torques_batch(a1mpc_handle* h, int B, const double* f_grf, const double* f_kin, const double* jac,

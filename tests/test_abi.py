@@ -42,7 +42,7 @@ def test_default_config_is_the_launch_default(a1):
 
 def test_argument_validation_happens_before_the_device_probe(a1):
     h = C.c_void_p()
-    for kw in (dict(horizon=7), dict(precision=32), dict(fz_min=1.0), dict(mu=0.0), dict(r=[0.0] * 12)):
+    for kw in (dict(horizon=7), dict(precision=16), dict(fz_min=1.0), dict(mu=0.0), dict(r=[0.0] * 12)):
         rc = a1.lib().a1mpc_create(C.byref(h), C.byref(a1.default_config(**kw)), 0)
         assert rc == -1 and a1.lib().a1mpc_last_error()
 
