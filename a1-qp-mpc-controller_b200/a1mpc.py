@@ -21,7 +21,8 @@ EXPORTS = [
     "a1mpc_grf_qp_batch", "a1mpc_joint_torques_batch", "a1mpc_leg_kinematics_batch", "a1mpc_ekf_bytes", "a1mpc_ekf_init_batch", "a1mpc_ekf_update_batch", "a1mpc_update_plan_batch", "a1mpc_device_alloc", "a1mpc_device_free", "a1mpc_host_alloc", "a1mpc_host_free",
     "a1mpc_memcpy_h2d", "a1mpc_memcpy_d2h", "a1mpc_sync", "a1mpc_event_create", "a1mpc_event_destroy",
     "a1mpc_event_record", "a1mpc_event_elapsed_ms", "a1mpc_launch_count", "a1mpc_measure_fp64_peak",
-    "a1mpc_flush_l2", "a1mpc_profile_begin", "a1mpc_profile_end", "a1mpc_nccl_unique_id", "a1mpc_nccl_init", "a1mpc_allgather_forces", "a1mpc_gen_states", "a1mpc_gen_schedule",
+    "a1mpc_flush_l2", "a1mpc_profile_begin", "a1mpc_profile_end", "a1mpc_nccl_unique_id", "a1mpc_nccl_init", "a1mpc_allgather_forces",
+    "a1mpc_qp_rollout_batch", "a1mpc_peer_gather_create", "a1mpc_peer_gather_connect", "a1mpc_peer_gather_buffer", "a1mpc_peer_gather_wait", "a1mpc_peer_gather_status", "a1mpc_peer_gather_destroy", "a1mpc_gen_states", "a1mpc_gen_schedule",
 ]
 
 
@@ -86,6 +87,12 @@ def lib():
             getattr(l, name).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         l.a1mpc_sync.argtypes = [C.c_void_p]
         l.a1mpc_flush_l2.argtypes = [C.c_void_p]
+        l.a1mpc_peer_gather_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        l.a1mpc_peer_gather_connect.argtypes = [C.c_void_p, C.c_char_p]
+        l.a1mpc_peer_gather_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        l.a1mpc_peer_gather_wait.argtypes = [C.c_void_p]
+        l.a1mpc_peer_gather_status.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        l.a1mpc_peer_gather_destroy.argtypes = [C.c_void_p]
         l.a1mpc_destroy.argtypes = [C.c_void_p]
         l.a1mpc_event_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         l.a1mpc_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
@@ -103,6 +110,7 @@ def lib():
         l.a1mpc_gen_schedule.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         l.a1mpc_build_qp_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(Inputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         l.a1mpc_qp_mats_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6
+        l.a1mpc_qp_rollout_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
         l.a1mpc_solve_dense_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
         l.a1mpc_grf_qp_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
         l.a1mpc_joint_torques_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
@@ -293,6 +301,15 @@ class Engine:
         _check(lib().a1mpc_qp_mats_batch(self.h, B, _p(A_d), _p(B_d_list), _p(x0), _p(x_d), _p(H), _p(g)))
         return H, g
 
+    def qp_rollout(self, A_d, B_d_list, x0, x_d):
+        """a1mpc_qp_rollout_batch: A_qp [B,13N,13], B_qp [B,13N,12N], H, g"""
+        A_d = np.ascontiguousarray(A_d, dtype=np.float64); B_d_list = np.ascontiguousarray(B_d_list, dtype=np.float64)
+        x0 = np.ascontiguousarray(x0, dtype=np.float64); x_d = np.ascontiguousarray(x_d, dtype=np.float64)
+        B = A_d.shape[0]; N = self.cfg.horizon; n = 12 * N
+        Aq = np.zeros((B, 13 * N, 13)); Bq = np.zeros((B, 13 * N, n)); H = np.zeros((B, n, n)); g = np.zeros((B, n))
+        _check(lib().a1mpc_qp_rollout_batch(self.h, B, _p(A_d), _p(B_d_list), _p(x0), _p(x_d), _p(Aq), _p(Bq), _p(H), _p(g)))
+        return Aq, Bq, H, g
+
     def solve_dense(self, H, g, contact):
         H = np.ascontiguousarray(H, dtype=np.float64); g = np.ascontiguousarray(g, dtype=np.float64)
         contact = np.ascontiguousarray(contact, dtype=np.uint32)
@@ -422,6 +439,34 @@ class Engine:
 
     def allgather_forces(self, f_local_ptr, f_all_ptr, B_local):
         _check(lib().a1mpc_allgather_forces(self.h, f_local_ptr, f_all_ptr, B_local))
+
+    # ---- fused final collect over peer memory (one process per GPU) ----
+    def peer_gather_create(self, nranks, rank, B_local):
+        """allocates this rank's gathered buffer; returns the 64-byte CUDA IPC handle to hand to the other ranks"""
+        hd = (C.c_char * 64)()
+        _check(lib().a1mpc_peer_gather_create(self.h, int(nranks), int(rank), int(B_local), hd))
+        return bytes(hd.raw)
+
+    def peer_gather_connect(self, handles):
+        """handles: the ranks' 64-byte handles in rank order (list of bytes)"""
+        blob = b"".join(handles)
+        _check(lib().a1mpc_peer_gather_connect(self.h, C.c_char_p(blob)))
+
+    def peer_gather_buffer(self):
+        p = C.c_void_p()
+        _check(lib().a1mpc_peer_gather_buffer(self.h, C.byref(p)))
+        return p
+
+    def peer_gather_wait(self):
+        _check(lib().a1mpc_peer_gather_wait(self.h))
+
+    def peer_gather_status(self):
+        v = C.c_int()
+        _check(lib().a1mpc_peer_gather_status(self.h, C.byref(v)))
+        return v.value
+
+    def peer_gather_destroy(self):
+        _check(lib().a1mpc_peer_gather_destroy(self.h))
 
     def flush_l2(self):
         _check(lib().a1mpc_flush_l2(self.h))

@@ -75,6 +75,17 @@ struct a1mpc_handle {
   cudaStream_t gather_stream = nullptr;   // the optional final collect runs here, overlapped with the next step's solve
   cudaEvent_t ev_gather_in = nullptr, ev_gather_done = nullptr;
   bool gather_pending = false;
+  // fused final collect over peer memory (a1mpc_peer_gather_*)
+  struct PeerGather {
+    bool connected = false;
+    int nranks = 0, rank = 0;
+    size_t B = 0;
+    void* local = nullptr;                 // this rank's allocation: [nranks][12][B] doubles, then nranks u64 step flags, then an int error word
+    double* buf[MAX_PEERS] = {nullptr};    // every rank's gathered buffer as mapped into this process (buf[rank] == local)
+    unsigned long long* flags[MAX_PEERS] = {nullptr};
+    bool opened[MAX_PEERS] = {false};
+    unsigned long long step = 0;
+  } peer;
 };
 
 namespace {
@@ -145,7 +156,29 @@ bool is_device_ptr(const void* p) {
 }
 
 // enqueue the fused path on device-resident SoA data
-int enqueue_solve(a1mpc_handle* h, int B, const DevInputs& din, const DevOutputs& dout, uint32_t* warm = nullptr, int shift = 0) {
+void attach_peers(a1mpc_handle* h, int B, DevOutputs& d) {
+  d.npeer = 0; d.rank = 0; d.peer_ld = 0;
+  for (int p = 0; p < MAX_PEERS; ++p) d.peer[p] = nullptr;
+  if (h->peer.connected && (size_t)B == h->peer.B) {
+    d.npeer = h->peer.nranks; d.rank = h->peer.rank; d.peer_ld = h->peer.B;
+    for (int p = 0; p < h->peer.nranks; ++p) d.peer[p] = h->peer.buf[p];
+  }
+}
+
+int peer_signal(a1mpc_handle* h, int B) {
+  if (!(h->peer.connected && (size_t)B == h->peer.B)) return A1MPC_OK;
+  PeerFlags pf;
+  for (int p = 0; p < MAX_PEERS; ++p) pf.p[p] = h->peer.flags[p];
+  h->peer.step++;
+  peer_signal_kernel<<<1, 32, 0, h->stream>>>(pf, h->peer.nranks, h->peer.rank, h->peer.step);
+  h->launches++;
+  CK(cudaGetLastError());
+  return A1MPC_OK;
+}
+
+int enqueue_solve(a1mpc_handle* h, int B, const DevInputs& din, const DevOutputs& dout_in, uint32_t* warm = nullptr, int shift = 0) {
+  DevOutputs dout = dout_in;
+  attach_peers(h, B, dout);
   CK(cudaMemsetAsync(h->d_count, 0, 8 * sizeof(int), h->stream));
   pack_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(din, B, h->d_rec, (int)h->cap, h->d_count, dout, h->cfg.horizon);
   h->launches++;
@@ -170,7 +203,7 @@ int enqueue_solve(a1mpc_handle* h, int B, const DevInputs& din, const DevOutputs
   }
   if (h->prof_on && h->prof_n < h->prof_cap) h->prof_n++;
   CK(cudaGetLastError());
-  return A1MPC_OK;
+  return peer_signal(h, B);   // fused collect: publish this call's step number to every rank (no-op when not connected)
 }
 
 int copy_rows(cudaStream_t st, void* dst, size_t dst_ld, const void* src, size_t src_ld, int rows, size_t B, size_t esz, cudaMemcpyKind kind) {
@@ -284,6 +317,7 @@ int a1mpc_destroy(a1mpc_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->gather_stream) cudaStreamSynchronize(h->gather_stream);
   if (h->nccl_comm) { a1mpc_internal_nccl_destroy(h->nccl_comm); h->nccl_comm = nullptr; }   // before its streams go away
+  a1mpc_peer_gather_destroy(h);
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(h->d_rec); fr(h->d_count); fr(h->d_x0); fr(h->d_rot); fr(h->d_foot); fr(h->d_ref); fr(h->d_f); fr(h->d_u);
   fr(h->d_contact); fr(h->d_status); fr(h->d_iters); fr(h->d_side); fr(h->d_flush); fr(h->d_lists);
@@ -424,6 +458,7 @@ int a1mpc_solve_batch_ext(a1mpc_handle* h, int B, const a1mpc_inputs* in, const 
     di = DevInputs{h->d_x0, h->d_rot, h->d_foot, h->d_ref, h->d_contact, Bs, f32};
     dout = DevOutputs{h->d_f, h->d_status, out->iters ? h->d_iters : nullptr, out->u_full ? h->d_u : nullptr, Bs, f32};
   }
+  attach_peers(h, -1, dout);   // the fused collect is wired to a1mpc_solve_batch / _warm only
   CK(cudaMemsetAsync(h->d_count, 0, 8 * sizeof(int), h->stream));
   if (h->ext_compact && dsched) {
     pack_ext2_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(di, dsched, dnorm, B, h->d_rec_ext, (int)h->cap_ext, h->d_count, dout, N);
@@ -490,41 +525,60 @@ int a1mpc_build_qp_batch(a1mpc_handle* h, int B, const a1mpc_inputs* in, double*
   return A1MPC_OK;
 }
 
-int a1mpc_qp_mats_batch(a1mpc_handle* h, int B, const double* A_d, const double* B_d_list, const double* x0, const double* x_d,
-                        double* H, double* g) {
-  if (!h || !A_d || !B_d_list || !x0 || !x_d || (!H && !g)) return fail(A1MPC_EINVAL, "null argument");
+static int qp_mats_impl(a1mpc_handle* h, int B, const double* A_d, const double* B_d_list, const double* x0, const double* x_d,
+                        double* H, double* g, double* A_qp, double* B_qp) {
+  if (!h || !A_d || !B_d_list || !x0 || !x_d || (!H && !g && !A_qp && !B_qp)) return fail(A1MPC_EINVAL, "null argument");
   if (B <= 0) return fail(A1MPC_EINVAL, "B must be positive");
   CK(cudaSetDevice(h->device));
   const int N = h->cfg.horizon, n = 12 * N;
   const bool dev = is_device_ptr(A_d);
+  {
+    const void* all_ptrs[] = {B_d_list, x0, x_d, H, g, A_qp, B_qp};
+    for (const void* q : all_ptrs)
+      if (q && is_device_ptr(q) != dev) return fail(A1MPC_EINVAL, "inputs and outputs must be all-host or all-device");
+  }
   const size_t Bs = (size_t)B;
-  const size_t szA = Bs * 169, szB = Bs * 13 * N * 12, szx0 = Bs * 13, szxd = Bs * 13 * N, szH = Bs * n * n, szg = Bs * n;
+  const size_t szA = Bs * 169, szB = Bs * 13 * N * 12, szx0 = Bs * 13, szxd = Bs * 13 * N, szH = H ? Bs * n * n : 0, szg = g ? Bs * n : 0;
+  const size_t szAq = A_qp ? Bs * 13 * N * 13 : 0, szBq = B_qp ? Bs * 13 * N * n : 0;
   const double *dA = A_d, *dB = B_d_list, *dx0 = x0, *dxd = x_d;
-  double *dH = H, *dg = g;
+  double *dH = H, *dg = g, *dAq = A_qp, *dBq = B_qp;
   int rc;
   if (!dev) {
-    if ((rc = ensure_side(h, (szA + szB + szx0 + szxd + szH + szg) * 8))) return rc;
+    if ((rc = ensure_side(h, (szA + szB + szx0 + szxd + szH + szg + szAq + szBq) * 8))) return rc;
     double* p = (double*)h->d_side;
     CK(cudaMemcpyAsync(p, A_d, szA * 8, cudaMemcpyHostToDevice, h->stream)); dA = p; p += szA;
     CK(cudaMemcpyAsync(p, B_d_list, szB * 8, cudaMemcpyHostToDevice, h->stream)); dB = p; p += szB;
     CK(cudaMemcpyAsync(p, x0, szx0 * 8, cudaMemcpyHostToDevice, h->stream)); dx0 = p; p += szx0;
     CK(cudaMemcpyAsync(p, x_d, szxd * 8, cudaMemcpyHostToDevice, h->stream)); dxd = p; p += szxd;
-    dH = p; p += szH;
-    dg = p;
-  } else if (!H || !g) {
-    return fail(A1MPC_EINVAL, "device-pointer calls need both H and g");
+    if (H) { dH = p; p += szH; }
+    if (g) { dg = p; p += szg; }
+    if (A_qp) { dAq = p; p += szAq; }
+    if (B_qp) { dBq = p; p += szBq; }
   }
   {
-    cudaError_t e = dense_qp_mats_launch(h->P, B, dA, dB, dx0, dxd, dH, dg, h->stream);
+    cudaError_t e = dense_qp_mats_launch(h->P, B, dA, dB, dx0, dxd, dH, dg, dAq, dBq, h->stream);
     if (e != cudaSuccess) return fail(A1MPC_ECUDA, std::string("qp_mats kernel: ") + cudaGetErrorString(e));
     h->launches += 1;
   }
   if (!dev) {
     if (H) CK(cudaMemcpyAsync(H, dH, szH * 8, cudaMemcpyDeviceToHost, h->stream));
     if (g) CK(cudaMemcpyAsync(g, dg, szg * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (A_qp) CK(cudaMemcpyAsync(A_qp, dAq, szAq * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (B_qp) CK(cudaMemcpyAsync(B_qp, dBq, szBq * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
   return A1MPC_OK;
+}
+
+int a1mpc_qp_mats_batch(a1mpc_handle* h, int B, const double* A_d, const double* B_d_list, const double* x0, const double* x_d,
+                        double* H, double* g) {
+  if (!H && !g) return fail(A1MPC_EINVAL, "null argument");
+  return qp_mats_impl(h, B, A_d, B_d_list, x0, x_d, H, g, nullptr, nullptr);
+}
+
+int a1mpc_qp_rollout_batch(a1mpc_handle* h, int B, const double* A_d, const double* B_d_list, const double* x0, const double* x_d,
+                           double* A_qp, double* B_qp, double* H, double* g) {
+  return qp_mats_impl(h, B, A_d, B_d_list, x0, x_d, H, g, A_qp, B_qp);
 }
 
 int a1mpc_solve_dense_batch(a1mpc_handle* h, int B, const double* H, const double* g, const uint32_t* contact, double* u, int32_t* status) {
@@ -980,6 +1034,91 @@ int a1mpc_flush_l2(a1mpc_handle* h) {
   flush_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(h->d_flush, h->flush_elems, 1.0);
   h->launches++;
   CK(cudaGetLastError());
+  return A1MPC_OK;
+}
+
+/* ---- fused final collect over peer memory (one process per GPU, CUDA IPC) ------------------------------------------------ */
+int a1mpc_peer_gather_create(a1mpc_handle* h, int nranks, int rank, int B_local, void* ipc_handle64) {
+  if (!h || !ipc_handle64 || nranks < 1 || nranks > MAX_PEERS || rank < 0 || rank >= nranks || B_local <= 0) return fail(A1MPC_EINVAL, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t");
+  CK(cudaSetDevice(h->device));
+  a1mpc_peer_gather_destroy(h);
+  auto& pg = h->peer;
+  const size_t fbytes = (size_t)nranks * 12 * (size_t)B_local * 8;
+  const size_t bytes = fbytes + (size_t)MAX_PEERS * 8 + 64;
+  CK(cudaMalloc(&pg.local, bytes));
+  CK(cudaMemset(pg.local, 0, bytes));
+  pg.nranks = nranks; pg.rank = rank; pg.B = (size_t)B_local; pg.step = 0;
+  pg.buf[rank] = (double*)pg.local;
+  pg.flags[rank] = (unsigned long long*)((char*)pg.local + fbytes);
+  cudaIpcMemHandle_t hd;
+  CK(cudaIpcGetMemHandle(&hd, pg.local));
+  std::memcpy(ipc_handle64, &hd, 64);
+  return A1MPC_OK;
+}
+
+int a1mpc_peer_gather_connect(a1mpc_handle* h, const void* all_handles) {
+  if (!h || !all_handles) return fail(A1MPC_EINVAL, "null argument");
+  auto& pg = h->peer;
+  if (!pg.local) return fail(A1MPC_EINVAL, "a1mpc_peer_gather_create first");
+  CK(cudaSetDevice(h->device));
+  const size_t fbytes = (size_t)pg.nranks * 12 * pg.B * 8;
+  for (int p = 0; p < pg.nranks; ++p) {
+    if (p == pg.rank) continue;
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, (const char*)all_handles + 64 * (size_t)p, 64);
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(A1MPC_ECUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(p) + "): " + cudaGetErrorString(e));
+    pg.buf[p] = (double*)ptr;
+    pg.flags[p] = (unsigned long long*)((char*)ptr + fbytes);
+    pg.opened[p] = true;
+  }
+  pg.connected = true;
+  return A1MPC_OK;
+}
+
+int a1mpc_peer_gather_buffer(a1mpc_handle* h, double** f_all) {
+  if (!h || !f_all) return fail(A1MPC_EINVAL, "null argument");
+  if (!h->peer.local) return fail(A1MPC_EINVAL, "a1mpc_peer_gather_create first");
+  *f_all = (double*)h->peer.local;
+  return A1MPC_OK;
+}
+
+int a1mpc_peer_gather_wait(a1mpc_handle* h) {
+  if (!h) return fail(A1MPC_EINVAL, "null argument");
+  auto& pg = h->peer;
+  if (!pg.connected) return fail(A1MPC_EINVAL, "a1mpc_peer_gather_connect first");
+  CK(cudaSetDevice(h->device));
+  int* err = (int*)((char*)pg.local + (size_t)pg.nranks * 12 * pg.B * 8 + (size_t)MAX_PEERS * 8);
+  peer_wait_kernel<<<1, 32, 0, h->stream>>>(pg.flags[pg.rank], pg.nranks, pg.step, (long long)4e9 /* ~2 s */, err);
+  h->launches++;
+  CK(cudaGetLastError());
+  return A1MPC_OK;
+}
+
+int a1mpc_peer_gather_status(a1mpc_handle* h, int* timed_out_rank_plus_1) {
+  if (!h || !timed_out_rank_plus_1) return fail(A1MPC_EINVAL, "null argument");
+  auto& pg = h->peer;
+  if (!pg.local) return fail(A1MPC_EINVAL, "a1mpc_peer_gather_create first");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(timed_out_rank_plus_1, (char*)pg.local + (size_t)pg.nranks * 12 * pg.B * 8 + (size_t)MAX_PEERS * 8, sizeof(int), cudaMemcpyDeviceToHost));
+  return A1MPC_OK;
+}
+
+int a1mpc_peer_gather_destroy(a1mpc_handle* h) {
+  if (!h) return A1MPC_OK;
+  auto& pg = h->peer;
+  if (!pg.local) return A1MPC_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int p = 0; p < MAX_PEERS; ++p) {
+    if (pg.opened[p] && pg.buf[p]) cudaIpcCloseMemHandle(pg.buf[p]);
+    pg.opened[p] = false; pg.buf[p] = nullptr; pg.flags[p] = nullptr;
+  }
+  cudaFree(pg.local);
+  pg.local = nullptr; pg.connected = false; pg.nranks = 0; pg.B = 0;
   return A1MPC_OK;
 }
 

@@ -20,7 +20,8 @@ namespace a1mpc {
 template <int N>
 __global__ void __launch_bounds__(256) qp_mats_kernel(const __grid_constant__ DevParams P, int B, const double* __restrict__ A_d,
                                                       const double* __restrict__ B_list, const double* __restrict__ x0,
-                                                      const double* __restrict__ x_d, double* __restrict__ H, double* __restrict__ g) {
+                                                      const double* __restrict__ x_d, double* __restrict__ H, double* __restrict__ g,
+                                                      double* __restrict__ Aqp, double* __restrict__ Bqp) {
   A1MPC_DYN_SMEM(sm);
   double* Apow = sm;                 // N x 169 : A_d^{k+1}
   double* W = Apow + N * 169;        // N x 13 x 12 : row block i of B_qp
@@ -32,8 +33,11 @@ __global__ void __launch_bounds__(256) qp_mats_kernel(const __grid_constant__ De
   constexpr int n = 12 * N;
   const double* Ad = A_d + (size_t)b * 169;
   const double* Bl = B_list + (size_t)b * 13 * N * 12;
-  double* Hb = H + (size_t)b * n * n;
-  double* gb = g + (size_t)b * n;
+  double* Hb = H ? H + (size_t)b * n * n : nullptr;
+  double* gb = g ? g + (size_t)b * n : nullptr;
+  // optional: the public ConvexMpc members A_qp [13N x 13] and B_qp [13N x 12N] (ConvexMpc.h:77-78), row-major, QP-major
+  double* Aq = Aqp ? Aqp + (size_t)b * 13 * N * 13 : nullptr;
+  double* Bq = Bqp ? Bqp + (size_t)b * 13 * N * n : nullptr;
   for (int e = tid; e < 169; e += blockDim.x) Apow[e] = Ad[e];
   __syncthreads();
   for (int i = 0; i < N; ++i) {
@@ -65,7 +69,15 @@ __global__ void __launch_bounds__(256) qp_mats_kernel(const __grid_constant__ De
       qe[tid] = (s - x_d[(size_t)b * 13 * N + 13 * i + tid]) * P.q2[tid];
     }
     __syncthreads();
+    if (Aq)
+      for (int e = tid; e < 169; e += blockDim.x) Aq[(size_t)i * 169 + e] = Apow[i * 169 + e];
+    if (Bq)
+      for (int e = tid; e < 13 * n; e += blockDim.x) {   // row block i: W for the block columns j <= i, zero to the right (:70-108 reset)
+        const int r = e / n, cc = e - n * r, j = cc / 12, c = cc - 12 * j;
+        Bq[(size_t)(13 * i + r) * n + cc] = (j <= i) ? W[j * 156 + r * 12 + c] : 0.0;
+      }
     const int ni = 12 * (i + 1);
+    if (Hb)
     for (int e = tid; e < ni * ni; e += blockDim.x) {
       const int r = e / ni, c = e - ni * r;
       const int j1 = r / 12, a = r - 12 * j1, j2 = c / 12, bb = c - 12 * j2;
@@ -79,6 +91,7 @@ __global__ void __launch_bounds__(256) qp_mats_kernel(const __grid_constant__ De
       if (mx == i) *dst = s + ((r == c) ? P.r2[a] : 0.0);
       else *dst += s;
     }
+    if (gb)
     for (int r = tid; r < ni; r += blockDim.x) {
       const int j1 = r / 12, a = r - 12 * j1;
       const double* w1 = W + j1 * 156 + a;
@@ -360,9 +373,9 @@ cudaError_t dense_setup(int horizon) {
 }
 
 cudaError_t dense_qp_mats_launch(const DevParams& P, int B, const double* A_d, const double* B_d_list, const double* x0, const double* x_d,
-                                 double* H, double* g, cudaStream_t st) {
-  if (P.N == 10) qp_mats_kernel<10><<<B, 256, qp_mats_smem<10>(), st>>>(P, B, A_d, B_d_list, x0, x_d, H, g);
-  else qp_mats_kernel<20><<<B, 256, qp_mats_smem<20>(), st>>>(P, B, A_d, B_d_list, x0, x_d, H, g);
+                                 double* H, double* g, double* A_qp, double* B_qp, cudaStream_t st) {
+  if (P.N == 10) qp_mats_kernel<10><<<B, 256, qp_mats_smem<10>(), st>>>(P, B, A_d, B_d_list, x0, x_d, H, g, A_qp, B_qp);
+  else qp_mats_kernel<20><<<B, 256, qp_mats_smem<20>(), st>>>(P, B, A_d, B_d_list, x0, x_d, H, g, A_qp, B_qp);
   return cudaGetLastError();
 }
 

@@ -32,7 +32,7 @@ cudaError_t build_dense_launch(const DevParams& P, const DevInputs& in, int B, d
 cudaError_t dense_setup(int horizon);
 // scratch: (4*B + 8) ints
 cudaError_t dense_qp_mats_launch(const DevParams& P, int B, const double* A_d, const double* B_d_list, const double* x0, const double* x_d,
-                                 double* H, double* g, cudaStream_t st);
+                                 double* H, double* g, double* A_qp, double* B_qp, cudaStream_t st);
 // returns cudaErrorInvalidValue for configurations whose factor does not fit (N=20 with >2 stance feet)
 cudaError_t dense_solve_launch(const DevParams& P, int sm_count, int B, const double* H, const double* g, const uint32_t* contact, double* u,
                                int32_t* status, int* scratch, cudaStream_t st, int* nlaunch);

@@ -142,10 +142,12 @@ __global__ void __launch_bounds__(32 * WPC) solve_kernel_sched2(const __grid_con
   if (A1MPC_RV && WPC > 1 && threadIdx.x == 0) mbar_init(smem + 2 * N * N, WPC);
   __syncthreads();
   const int nq = count[6];
-  // QP q -> warp (q / gridDim.x) of CTA (q % gridDim.x): a class with fewer QPs than the grid has CTAs runs ONE warp per SM
-  // (its neighbours find no work and leave the rendezvous at once), so that at B ~ 1000 the slowest QP -- which is the step --
-  // has an SM's issue slots and instruction cache to itself; with full grids every warp is busy either way
-  const int gw = wib * gridDim.x + blockIdx.x, nw = gridDim.x * WPC;
+  // QP q -> warp q % WPC of CTA q / WPC: a class with few QPs fills few CTAs completely and leaves the other SMs to the classes that
+  // run concurrently on their own streams.  (Spreading one QP per CTA first was measured in round 2: a 4-stance CTA reserves its
+  // four warps' shared memory and registers whether or not they have work, the trot class lost 2/3 of the SMs to 102 QPs and took
+  // 0.43 instead of 0.25 ms at B = 1024, while the 4-stance kernel itself did not get faster -- its time is the slowest QP's
+  // factorisation count times a per-factorisation latency that one warp per scheduler already has to itself.)
+  const int gw = blockIdx.x * WPC + wib, nw = gridDim.x * WPC;
   uint32_t parity = 0;
 #pragma unroll 1
   for (int q = gw; q < nq; q += nw) {
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(32 * WPC) solve_kernel_sched2(const __grid_con
         for (int a = 0; a < 3; ++a) f[a] = c.rec[12 + a] * wx_ + c.rec[15 + a] * wy_ + c.rec[18 + a] * wz_;
       }
 #pragma unroll
-      for (int a = 0; a < 3; ++a) st_out(out.f_body, (size_t)(3 * lane + a) * out.ld + b, f[a], out.f32);
+      for (int a = 0; a < 3; ++a) st_force(out, (3 * lane + a), b, f[a]);
     }
     if (lane == 0) {
       out.status[b] = status;

@@ -28,7 +28,7 @@ static cudaError_t setup_n(int sm_count, ClassLaunch& c) {
 cudaError_t ext_setup(int horizon, int sm_count, ClassLaunch& c) { return horizon == 10 ? setup_n<10>(sm_count, c) : setup_n<20>(sm_count, c); }
 
 void ext_launch(int horizon, const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count, const DevOutputs& out) {
-  int grid = B;   // one QP per CTA first, at most the persistent grid
+  int grid = (B + c.wpc - 1) / c.wpc;
   if (grid > c.max_ctas) grid = c.max_ctas;
   if (grid < 1) grid = 1;
   if (horizon == 10) solve_kernel<4, 10, A1MPC_WPC34, 1, true><<<grid, 32 * A1MPC_WPC34, c.smem, st>>>(P, rec, count, out);
@@ -51,7 +51,7 @@ cudaError_t sched2_setup(int sm_count, ClassLaunch& c) {
 }
 
 void sched2_launch(const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count, const DevOutputs& out) {
-  int grid = B;   // one QP per CTA first, at most the persistent grid
+  int grid = (B + c.wpc - 1) / c.wpc;
   if (grid > c.max_ctas) grid = c.max_ctas;
   if (grid < 1) grid = 1;
   solve_kernel_sched2<10, 4><<<grid, 32 * 4, c.smem, st>>>(P, rec, count, out);

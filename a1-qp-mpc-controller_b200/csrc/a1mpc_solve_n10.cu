@@ -27,7 +27,7 @@ static cudaError_t setup_one_warm(const ClassLaunch& c) {
 template <int NS, int N, int WPC, int LSM>
 static void launch_one_warm(const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count,
                             const DevOutputs& out, uint32_t* warm, int shift) {
-  int grid = B;   // one QP per CTA first (see the q -> warp map in a1mpc_solve_body.inc), at most the persistent grid
+  int grid = (B + WPC - 1) / WPC;
   if (grid > c.max_ctas) grid = c.max_ctas;
   if (grid < 1) grid = 1;
   solve_kernel_warm<NS, N, WPC, LSM><<<grid, 32 * WPC, c.smem, st>>>(P, rec, count, out, warm, shift);
@@ -35,7 +35,7 @@ static void launch_one_warm(const ClassLaunch& c, cudaStream_t st, int B, const 
 
 template <int NS, int N, int WPC, int LSM>
 static void launch_one(const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count, const DevOutputs& out) {
-  int grid = B;   // one QP per CTA first (see the q -> warp map in a1mpc_solve_body.inc), at most the persistent grid
+  int grid = (B + WPC - 1) / WPC;
   if (grid > c.max_ctas) grid = c.max_ctas;
   if (grid < 1) grid = 1;
   solve_kernel<NS, N, WPC, LSM><<<grid, 32 * WPC, c.smem, st>>>(P, rec, count, out);
@@ -72,17 +72,24 @@ void fused_launch_n10(int ns, const ClassLaunch& c, cudaStream_t st, int B, cons
   if (ns == 4) launch_one<4, 10, A1MPC_WPC34, 1>(c, st, B, P, rec, count, out);
 }
 #else
+// warps per CTA of the N = 20 classes: 69.8 KB (NS = 2) / 117.8 KB (NS = 4, wrench) of shared memory per warp allow 3 / 1 per SM
+#ifndef A1MPC_N20_WPC1
+#define A1MPC_N20_WPC1 2
+#endif
+#ifndef A1MPC_N20_WPC2
+#define A1MPC_N20_WPC2 3   // one CTA of three warps with the rendezvous instead of three independent one-warp CTAs: trot N = 20 B = 16384
+#endif                     // 0.55 -> 0.79 M QPs/s on a B200 (profiles/r02b_*.txt): one instruction-cache fill serves the three warps
 cudaError_t fused_setup_n20(int sm_count, ClassLaunch (&cls)[5]) {
   cudaError_t e;
-  if ((e = setup_one<1, 20, 2, 0>(sm_count, cls[1])) != cudaSuccess) return e;
-  if ((e = setup_one<2, 20, 1, 0>(sm_count, cls[2])) != cudaSuccess) return e;
+  if ((e = setup_one<1, 20, A1MPC_N20_WPC1, 0>(sm_count, cls[1])) != cudaSuccess) return e;
+  if ((e = setup_one<2, 20, A1MPC_N20_WPC2, 0>(sm_count, cls[2])) != cudaSuccess) return e;
   if ((e = setup_one<3, 20, 1, 1>(sm_count, cls[3])) != cudaSuccess) return e;
   if ((e = setup_one<4, 20, 1, 1>(sm_count, cls[4])) != cudaSuccess) return e;
   return cudaSuccess;
 }
 void fused_launch_n20(int ns, const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count, const DevOutputs& out) {
-  if (ns == 1) launch_one<1, 20, 2, 0>(c, st, B, P, rec, count, out);
-  if (ns == 2) launch_one<2, 20, 1, 0>(c, st, B, P, rec, count, out);
+  if (ns == 1) launch_one<1, 20, A1MPC_N20_WPC1, 0>(c, st, B, P, rec, count, out);
+  if (ns == 2) launch_one<2, 20, A1MPC_N20_WPC2, 0>(c, st, B, P, rec, count, out);
   if (ns == 3) launch_one<3, 20, 1, 1>(c, st, B, P, rec, count, out);
   if (ns == 4) launch_one<4, 20, 1, 1>(c, st, B, P, rec, count, out);
 }

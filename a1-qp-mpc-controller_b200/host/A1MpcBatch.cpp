@@ -26,6 +26,20 @@ static a1mpc_config make_cfg(const double* q, const double* r, int horizon) {
 
 ConvexMpcBatch::ConvexMpcBatch(int batch, const double* q, const double* r, int horizon, int device)
     : B_(batch), N_(horizon), handle_(make_cfg(q, r, horizon), device) {
+  // what the reference's constructor builds (ConvexMpc.cpp:7-68): tiled weights, Q = 2q, R = 2r, the pyramid matrix
+  const int N = N_;
+  q_weights_mpc.resize(13 * N); r_weights_mpc.resize(12 * N); Q.resize(13 * N); R.resize(12 * N);
+  for (int i = 0; i < N; ++i) {
+    for (int k = 0; k < 13; ++k) { q_weights_mpc[13 * i + k] = q[k]; Q[13 * i + k] = 2 * q[k]; }
+    for (int k = 0; k < 12; ++k) { r_weights_mpc[12 * i + k] = r[k]; R[12 * i + k] = 2 * r[k]; }
+  }
+  const size_t nc = 12 * (size_t)N;
+  linear_constraints.assign(20 * (size_t)N * nc, 0.0);
+  for (int i = 0; i < NUM_LEG * N; ++i) {
+    auto at = [&](int row, int col) -> double& { return linear_constraints[(size_t)row * nc + col]; };
+    at(0 + 5 * i, 0 + 3 * i) = 1; at(1 + 5 * i, 0 + 3 * i) = 1; at(2 + 5 * i, 1 + 3 * i) = 1; at(3 + 5 * i, 1 + 3 * i) = 1; at(4 + 5 * i, 2 + 3 * i) = 1;
+    at(0 + 5 * i, 2 + 3 * i) = mu; at(1 + 5 * i, 2 + 3 * i) = -mu; at(2 + 5 * i, 2 + 3 * i) = mu; at(3 + 5 * i, 2 + 3 * i) = -mu;
+  }
   reset();
 }
 
@@ -34,6 +48,7 @@ void ConvexMpcBatch::reset() {
   A_mat_c.assign(B * 169, 0.0); B_mat_c.assign(B * 156, 0.0); A_mat_d.assign(B * 169, 0.0); B_mat_d.assign(B * 156, 0.0);
   B_mat_d_list.assign(B * 13 * N * 12, 0.0);
   hessian.assign(B * 12 * N * 12 * N, 0.0); gradient.assign(B * 12 * N, 0.0);
+  A_qp.assign(B * 13 * N * 13, 0.0); B_qp.assign(B * 13 * N * 12 * N, 0.0);
   lb.assign(B * 20 * N, 0.0); ub.assign(B * 20 * N, 0.0); solution.assign(B * 12 * N, 0.0);
   status.assign(B, 0);
   x0_.assign(B * 13, 0.0); xd_.assign(B * 13 * N, 0.0); contact_.assign(B, 0u);
@@ -99,8 +114,9 @@ void ConvexMpcBatch::set_states(int b, const double* mpc_states, const double* m
 }
 
 void ConvexMpcBatch::calculate_qp_mats() {
-  check(a1mpc_qp_mats_batch(handle_.h, B_, A_mat_d.data(), B_mat_d_list.data(), x0_.data(), xd_.data(), hessian.data(), gradient.data()),
-        "a1mpc_qp_mats_batch");
+  check(a1mpc_qp_rollout_batch(handle_.h, B_, A_mat_d.data(), B_mat_d_list.data(), x0_.data(), xd_.data(), A_qp.data(), B_qp.data(),
+                               hessian.data(), gradient.data()),
+        "a1mpc_qp_rollout_batch");
   // bounds, ConvexMpc.cpp:223-245 (host: 40N scalars per robot)
   const double INFTY = 1e30;  // OsqpEigen::INFTY
   for (int b = 0; b < B_; ++b)
@@ -180,6 +196,31 @@ void A1RobotControlBatch::compute_grf(const std::vector<A1CtrlStatesLite>& st, d
     for (int leg = 0; leg < 4; ++leg)
       for (int a = 0; a < 3; ++a) out[b][a * 4 + leg] = f_[(3 * leg + a) * B + b];  // 3 x NUM_LEG, row-major
   if (status) *status = status_;
+}
+
+void A1RobotControlBatch::compute_grf(std::vector<A1CtrlStatesLite>& st, double dt, std::vector<std::array<double, 12>>& out,
+                                      std::vector<int32_t>* status) {
+  compute_grf(static_cast<const std::vector<A1CtrlStatesLite>&>(st), dt, out, status);
+  // state write-backs of the reference (A1RobotControl.cpp:452-488); the same scalars the pack kernel forms on the device
+  const int N = cfg_.horizon;
+  for (A1CtrlStatesLite& s : st) {
+    for (int k = 0; k < 3; ++k) {
+      s.mpc_states[k] = s.root_euler[k]; s.mpc_states[3 + k] = s.root_pos[k];
+      s.mpc_states[6 + k] = s.root_ang_vel[k]; s.mpc_states[9 + k] = s.root_lin_vel[k];
+    }
+    s.mpc_states[12] = -9.8;
+    for (int a = 0; a < 3; ++a)
+      s.root_lin_vel_d_world[a] = s.root_rot_mat[3 * a] * s.root_lin_vel_d[0] + s.root_rot_mat[3 * a + 1] * s.root_lin_vel_d[1] + s.root_rot_mat[3 * a + 2] * s.root_lin_vel_d[2];
+    s.mpc_states_d.resize(13 * (size_t)N);
+    for (int i = 0; i < N; ++i) {
+      double* d = &s.mpc_states_d[13 * (size_t)i];
+      d[0] = s.root_euler_d[0]; d[1] = s.root_euler_d[1]; d[2] = s.root_euler[2] + s.root_ang_vel_d[2] * dt * (i + 1);
+      d[3] = s.root_pos[0] + s.root_lin_vel_d_world[0] * dt * (i + 1); d[4] = s.root_pos[1] + s.root_lin_vel_d_world[1] * dt * (i + 1);
+      d[5] = s.root_pos_d[2];
+      d[6] = s.root_ang_vel_d[0]; d[7] = s.root_ang_vel_d[1]; d[8] = s.root_ang_vel_d[2];
+      d[9] = s.root_lin_vel_d_world[0]; d[10] = s.root_lin_vel_d_world[1]; d[11] = 0; d[12] = -9.8;
+    }
+  }
 }
 
 }  // namespace a1mpc_host

@@ -31,6 +31,10 @@ struct A1CtrlStatesLite {
   double foot_pos_abs[12] = {0};                         // 3 x NUM_LEG, row-major like Eigen's operator<< listing
   double root_euler_d[3] = {0, 0, 0}, root_pos_d[3] = {0, 0, 0}, root_lin_vel_d[3] = {0, 0, 0}, root_ang_vel_d[3] = {0, 0, 0};
   bool contacts[NUM_LEG] = {false, false, false, false};
+  // written by compute_grf, as the reference writes them into A1CtrlStates (A1RobotControl.cpp:452-488):
+  double mpc_states[MPC_STATE_DIM] = {0};              // [euler, pos, ang_vel, lin_vel, -9.8]
+  std::vector<double> mpc_states_d;                    // 13 * horizon desired states
+  double root_lin_vel_d_world[3] = {0, 0, 0};          // root_rot_mat * root_lin_vel_d
 };
 
 struct Handle {
@@ -63,6 +67,11 @@ class ConvexMpcBatch {
   int horizon() const { return N_; }
   // public result members, QP-major (ConvexMpc.h:87-93): hessian [B][12N][12N], gradient [B][12N], lb/ub [B][20N]
   std::vector<double> hessian, gradient, lb, ub, solution;
+  // the other public members of the reference class (its `private:` is commented out, ConvexMpc.h:37):
+  //   A_qp [B][13N][13], B_qp [B][13N][12N] (ConvexMpc.h:77-78; filled by calculate_qp_mats on the GPU),
+  //   linear_constraints [20N][12N] (the constant pyramid matrix, ConvexMpc.cpp:46-58; dense row-major here, shared by the batch),
+  //   q_weights_mpc [13N], r_weights_mpc [12N] (tiled weights), Q = 2 q_weights_mpc, R = 2 r_weights_mpc (diagonals, ConvexMpc.cpp:20,41)
+  std::vector<double> A_qp, B_qp, linear_constraints, q_weights_mpc, r_weights_mpc, Q, R;
   std::vector<int32_t> status;
   // per-robot working matrices, row-major (ConvexMpc.h:68-76)
   std::vector<double> A_mat_c, B_mat_c, A_mat_d, B_mat_d, B_mat_d_list;
@@ -85,6 +94,9 @@ class A1RobotControlBatch {
   // foot_forces_grf: 3 x NUM_LEG per robot, row-major ([b][xyz][leg]), body frame -- what compute_grf returns
   // (A1RobotControl.cpp:563).  dt is mpc_dt when use_sim_time == "true" (A1RobotControl.cpp:465-467), else pass 0.0025.
   void compute_grf(const std::vector<A1CtrlStatesLite>& states, double dt, std::vector<std::array<double, 12>>& foot_forces_grf,
+                   std::vector<int32_t>* status = nullptr);
+  // the same, and like the reference it leaves mpc_states, mpc_states_d and root_lin_vel_d_world in every state (A1RobotControl.cpp:452-488)
+  void compute_grf(std::vector<A1CtrlStatesLite>& states, double dt, std::vector<std::array<double, 12>>& foot_forces_grf,
                    std::vector<int32_t>* status = nullptr);
   // The reference's solver object persists and warm-starts every tick (A1RobotControl.h:67, A1RobotControl.cpp:522-538).
   // true: robot b of consecutive compute_grf calls is the same robot, and its previous active faces are tried first

@@ -144,40 +144,226 @@ def dist_bcast_bytes(dist, payload, rank):
     return obj[0]
 
 
-def cpu_reference_rate(cfg_kw, config_id, nthreads, target_seconds, O, a1mpc):
+def cpu_reference_rate(cfg_kw, config_id, nthreads, target_seconds, O):
     """reference path restated on CPU (dense build + OSQP-algorithm at default settings, cold start) on a bounded
     sample of the same synthetic workload (same generator, same distribution), sized for ~target_seconds"""
     ocfg = O.make_config(**cfg_kw)
     probe = 16 * nthreads
-    st = a1mpc.gen_states(probe, config_id, stream=777)
+    st = O.gen_states(probe, config_id, stream=777)
     sec, _ = O.time_reference_path(ocfg, O.Batch(st["x0"], st["rot"], st["foot"], st["ref"], st["contact"]), nthreads)
     rate = probe / max(sec, 1e-9)
     S = int(max(probe, min(rate * target_seconds, 4e6)))
-    st = a1mpc.gen_states(S, config_id, stream=778)
+    st = O.gen_states(S, config_id, stream=778)
     sec, _ = O.time_reference_path(ocfg, O.Batch(st["x0"], st["rot"], st["foot"], st["ref"], st["contact"]), nthreads)
     return S / sec, S, sec
 
 
+def dist_allgather_obj(dist, obj, world):
+    out = [None] * world
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def setup_collect(a1mpc, eng, dist, n_gpus, rank, B, mode):
+    """final collect of the forces.  "peer": the solve kernels store them straight into every rank's gathered buffer (CUDA IPC peer
+    mappings, stores over NVLink; a1mpc_peer_gather_*) -- a per-step wait on the step flags is all that is enqueued; "nccl": one
+    ncclAllGather per step on a side stream.  Returns (description, per-step function or None, error text or None)."""
+    err = None
+    if mode in ("auto", "peer"):
+        hd = None
+        try:
+            hd = eng.peer_gather_create(n_gpus, rank, B)
+        except Exception as e:
+            err = str(e)
+        handles = dist_allgather_obj(dist, hd, n_gpus)      # every rank takes part in both exchanges whatever happened locally
+        ok = 0
+        if all(x is not None for x in handles):
+            try:
+                eng.peer_gather_connect(handles)
+                ok = 1
+            except Exception as e:
+                err = str(e)
+        if all(dist_allgather_obj(dist, ok, n_gpus)):
+            return ("fused: solve-kernel epilogue stores into every rank's buffer over NVLink (CUDA IPC peer memory) + per-step flag wait",
+                    (lambda d: eng.peer_gather_wait()), None, eng.peer_gather_buffer())
+        try:
+            eng.peer_gather_destroy()
+        except Exception:
+            pass
+        err = err or "a peer rank could not map the buffers"
+        if mode == "peer":
+            return "unavailable", None, err, None
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            cand = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ.setdefault("A1MPC_NCCL_LIB", cand)
+        if not getattr(eng, "_nccl_ready", False):
+            uid = a1mpc.nccl_unique_id() if rank == 0 else None
+            uid = dist_bcast_bytes(dist, uid, rank)
+            eng.nccl_init(n_gpus, rank, uid)
+            eng._nccl_ready = True
+        gbuf = eng.dalloc(n_gpus * 12 * B * 8)
+        return "ncclAllGather of [12][B] forces per step" + (" (peer path unavailable: %s)" % err if err else ""), (lambda d: eng.allgather_forces(d.f_body, gbuf, B)), err, gbuf
+    except Exception as e:
+        return "unavailable", None, "%s; nccl: %s" % (err, e), None
+
+
+def verify_collect(a1mpc, eng, dist, n_gpus, rank, B, d, gbuf):
+    """after one more step + wait: block [p] of every rank's gathered buffer must be rank p's own f_body, bit for bit"""
+    eng.sync()
+    dist_barrier(dist)
+    f, _ = d.download()
+    mine = int(np.ascontiguousarray(f).view(np.uint64).sum(dtype=np.uint64))
+    sums = dist_allgather_obj(dist, mine, n_gpus)
+    g = np.zeros((n_gpus, 12, B), dtype=f.dtype)
+    a1mpc._check(a1mpc.lib().a1mpc_memcpy_d2h(eng.h, g.ctypes.data, gbuf, g.nbytes))
+    eng.sync()
+    ok = all(int(np.ascontiguousarray(g[p]).view(np.uint64).sum(dtype=np.uint64)) == sums[p] for p in range(n_gpus)) and np.array_equal(g[rank], f)
+    return bool(all(dist_allgather_obj(dist, bool(ok), n_gpus)))
+
+
+def timed_steps(eng, dist, step, K, W):
+    """W warm-up + exactly K timed steps, CUDA events on the handle's stream, barrier + synchronise on both sides, max over ranks"""
+    for i in range(W):
+        step(i)
+    eng.sync()
+    dist_barrier(dist)
+    e0, e1 = eng.event(), eng.event()
+    eng.record(e0)
+    for i in range(K):
+        step(W + i)
+    eng.record(e1)
+    eng.sync()
+    dist_barrier(dist)
+    return dist_max(dist, eng.elapsed_ms(e0, e1)) / K
+
+
+def _status_hist(a1mpc, eng, d, B):
+    st = np.zeros(B, dtype=np.int32)
+    a1mpc._check(a1mpc.lib().a1mpc_memcpy_d2h(eng.h, st.ctypes.data, d.status, st.nbytes))
+    eng.sync()
+    return {int(k): int(v) for k, v in zip(*np.unique(st, return_counts=True))}
+
+
+def subrecord_config3(a1mpc, local, K=20, W=3):
+    """BASELINE configs[2]: trot, N = 20, batch 8192, precision 32 (fp32 boundary arrays, fp64 + certificate inside), 1 GPU.
+    4 distinct device-resident batches, L2 flushed before every step (the flush, ~40 us, is inside the timed region: < 0.3 %)."""
+    B, N = 8192, 20
+    eng = a1mpc.Engine(a1mpc.default_config(horizon=N, precision=32), device=local)
+    dev = []
+    for r in range(4):
+        d = a1mpc.DeviceBatch(eng, B, want_u=False, want_iters=False)
+        d.upload(a1mpc.gen_states(B, 2, stream=3000 + r))
+        dev.append(d)
+
+    def step(i):
+        eng.flush_l2()
+        eng.solve_ptrs(B, dev[i % 4].inp, dev[i % 4].out)
+    ms = timed_steps(eng, None, step, K, W)
+    rec = {"workload": "trot gait convex MPC, horizon N=20 (240x240 condensed Hessian), batch 8192, precision 32 (BASELINE configs[2])",
+           "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": K, "warmup": W, "dtype": "f64 arithmetic, f32 boundary arrays (224 B/QP)",
+           "status_histogram": _status_hist(a1mpc, eng, dev[0], B), "cache": "4 distinct batches, L2 flushed before every step"}
+    eng.close()
+    return rec
+
+
+def subrecord_config4(a1mpc, local, K=20, W=3):
+    """BASELINE configs[3]: randomised contact schedules (trot / bound / rotary gallop) + terrain normals, batch 16384, fp64, 1 GPU
+    (an extension beyond the reference; a1mpc_solve_batch_ext with device-resident arrays)."""
+    import ctypes as C
+    B, N = 16384, 10
+    eng = a1mpc.Engine(a1mpc.default_config(horizon=N), device=local)
+    dev = []
+    for r in range(4):
+        d = a1mpc.DeviceBatch(eng, B, want_u=False, want_iters=False)
+        d.upload(a1mpc.gen_states(B, 4, stream=4000 + r))
+        sched, normals = a1mpc.gen_schedule(B, N, 4, 4000 + r)
+        d.sched = eng.dalloc(sched.nbytes); d.normals = eng.dalloc(normals.nbytes)
+        a1mpc._check(a1mpc.lib().a1mpc_memcpy_h2d(eng.h, d.sched, sched.ctypes.data, sched.nbytes))
+        a1mpc._check(a1mpc.lib().a1mpc_memcpy_h2d(eng.h, d.normals, normals.ctypes.data, normals.nbytes))
+        eng.sync()
+        d.ext = a1mpc.InputsExt(d.sched, d.normals)
+        dev.append(d)
+
+    def step(i):
+        d = dev[i % 4]
+        eng.flush_l2()
+        a1mpc._check(a1mpc.lib().a1mpc_solve_batch_ext(eng.h, B, C.byref(d.inp), C.byref(d.ext), C.byref(d.out)))
+    ms = timed_steps(eng, None, step, K, W)
+    rec = {"workload": "randomised contact schedule (trot/bound/gallop) + terrain normals, horizon N=10, batch 16384, fp64 (BASELINE configs[3])",
+           "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": K, "warmup": W, "dtype": "f64",
+           "status_histogram": _status_hist(a1mpc, eng, dev[0], B), "cache": "4 distinct batches, L2 flushed before every step"}
+    eng.close()
+    return rec
+
+
+def subrecord_config5(a1mpc, eng, dist, n_gpus, rank, collect_mode, K=30, W=3):
+    """BASELINE configs[4]: N = 10 trot, 32768 QPs per GPU (262144 at 8 GPUs), all-gather of the [12][B] forces after every step.
+    Every rank takes part (the collect is a collective); device time, max over ranks."""
+    B = 32768
+    dev = []
+    for r in range(4):
+        d = a1mpc.DeviceBatch(eng, B, want_u=False, want_iters=False)
+        d.upload(a1mpc.gen_states(B, 2, stream=5000 + rank * 1000003 + r))
+        dev.append(d)
+    desc, fn, err, gbuf = ("none", None, None, None)
+    if collect_mode:
+        try:
+            eng.peer_gather_destroy()
+        except Exception:
+            pass
+        desc, fn, err, gbuf = setup_collect(a1mpc, eng, dist, n_gpus, rank, B, collect_mode)
+
+    def step(i):
+        d = dev[i % 4]
+        eng.solve_ptrs(B, d.inp, d.out)
+        if fn is not None:
+            fn(d)
+    ms = timed_steps(eng, dist, step, K, W)
+    peer_status = None
+    try:
+        peer_status = eng.peer_gather_status()
+    except Exception:
+        pass
+    verified = None
+    if fn is not None:
+        step(0)
+        verified = verify_collect(a1mpc, eng, dist, n_gpus, rank, B, dev[0], gbuf)
+    rec = {"workload": "trot gait convex MPC, horizon N=10, batch 32768 per GPU = %d QPs per step, fp64 (BASELINE configs[4])" % (B * n_gpus),
+           "value": n_gpus * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": K, "warmup": W, "dtype": "f64", "n_gpus": n_gpus,
+           "final_collect": desc if fn is not None else ("none" if not collect_mode else "unavailable: %s" % err), "peer_wait_timeouts": peer_status, "final_collect_verified": verified,
+           "status_histogram_rank0": _status_hist(a1mpc, eng, dev[0], B),
+           "cache": "4 distinct batches per rank (4 x 11 MB in, outputs 3 MB): smaller than L2, the path is compute bound (440 B against ~1 MFLOP per QP)"}
+    for d in dev:
+        d.free()
+    return rec
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU algorithm (restated: Eigen/OSQP/ROS are not installable
-    offline, so oracle/_ref does not exist) on all host threads, same metric/config."""
+    """--impl reference: the reference's own CPU algorithm on all usable host cores, same metric/config.  kind "port": the oracle's
+    literal restatement (dense ConvexMpc build + OSQP-algorithm).  The reference's own ConvexMpc.cpp does compile here (oracle/_ref,
+    against the ref_shim header stand-ins) and pins the restatement, but its matrix products would run through the stand-in's plain
+    loops instead of Eigen's vectorised kernels, and OSQP itself is absent -- timing that build would misstate the reference."""
     from oracle import oracle_py as O
     rank, world, local, dist = dist_setup(args.gpus)
     if rank != 0:
         return
-    import a1mpc
-    nthreads = O.hardware_threads()
+    # threads = the cores this process can really use (cgroup quota / affinity), not hardware_concurrency
+    nthreads, core_info = O.effective_cores()
     B = args.batch
     cfg_kw = dict(horizon=args.horizon)
     ocfg = O.make_config(**cfg_kw)
     # bounded sample per step so that warmup+steps end within a few minutes
     probe = 16 * nthreads
-    stp = a1mpc.gen_states(probe, 2, 777)
+    stp = O.gen_states(probe, 2, 777)
     sec, _ = O.time_reference_path(ocfg, O.Batch(stp["x0"], stp["rot"], stp["foot"], stp["ref"], stp["contact"]), nthreads)
     rate = probe / max(sec, 1e-9)
     budget = 150.0 / max(1, args.steps + args.warmup)
     S = int(max(16 * nthreads, rate * min(budget, 4.0)))
-    st = a1mpc.gen_states(S, 2, 778)
+    st = O.gen_states(S, 2, 778)
     ob = O.Batch(st["x0"], st["rot"], st["foot"], st["ref"], st["contact"])
     for _ in range(args.warmup):
         O.time_reference_path(ocfg, ob, nthreads)
@@ -191,7 +377,7 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "trot gait convex MPC, horizon N=%d, batch %d per GPU, fp64 (BASELINE configs[1])" % (args.horizon, B),
                        "sample_qps_per_step": S},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port",
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "cores_detail": core_info, "kind": "port",
                              "sample": "%d synthetic QPs (same generator/distribution as the workload) per step, dense ConvexMpc build + OSQP-algorithm restatement at OSQP defaults, cold start, one QP per task" % S},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -210,6 +396,9 @@ def main():
     ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--collect", default="auto", choices=["auto", "peer", "nccl"], help="final collect for --gpus > 1")
+    ap.add_argument("--ring", type=int, default=0, help="number of distinct input batches (0: enough to exceed L2)")
+    ap.add_argument("--no-subrecords", action="store_true", help="skip the config3 / config4 / config5 sub-records")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -224,8 +413,9 @@ def main():
     eng = a1mpc.Engine(cfg, device=local)
 
     # ---- ring of distinct input batches, total bytes > L2 so that no step finds its inputs cached ----
-    ring = int(np.ceil(1.05 * L2_BYTES / (IN_BYTES_PER_QP * B)))
-    ring = max(2, min(ring, max(K, 2)))
+    ring = max(2, int(np.ceil(1.05 * L2_BYTES / (IN_BYTES_PER_QP * B))))     # independent of --steps
+    if args.ring > 0:
+        ring = args.ring                                                       # profiler runs: a short ring, labelled as such
     dev, host = [], []
     for r in range(ring):
         st = a1mpc.gen_states(B, args.config_id, stream=rank * 1000003 + r)
@@ -236,30 +426,16 @@ def main():
             host.append(st)
     ring_bytes = ring * IN_BYTES_PER_QP * B
 
-    # ---- optional final collect of the forces over NCCL (config 5) ----
-    gather = None
-    gather_err = None
+    # ---- final collect of the forces (config 5): fused peer stores, NCCL all-gather as the fallback ----
+    collect_desc, collect_fn, collect_err, collect_buf = "none", None, None, None
     if n_gpus > 1 and not args.no_gather:
-        try:
-            import importlib.util
-            spec = importlib.util.find_spec("nvidia.nccl")
-            if spec and spec.submodule_search_locations:
-                cand = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
-                if os.path.exists(cand):
-                    os.environ.setdefault("A1MPC_NCCL_LIB", cand)
-            uid = a1mpc.nccl_unique_id() if rank == 0 else None
-            uid = dist_bcast_bytes(dist, uid, rank)
-            eng.nccl_init(n_gpus, rank, uid)
-            gather = eng.dalloc(n_gpus * 12 * B * 8)
-        except Exception as e:  # reported, never silent
-            gather = None
-            gather_err = str(e)
+        collect_desc, collect_fn, collect_err, collect_buf = setup_collect(a1mpc, eng, dist, n_gpus, rank, B, args.collect)
 
     def step(i):
         d = dev[i % ring]
         eng.solve_ptrs(B, d.inp, d.out)
-        if gather is not None:
-            eng.allgather_forces(d.f_body, gather, B)
+        if collect_fn is not None:
+            collect_fn(d)
 
     # ---- warm-up ----
     for i in range(W):
@@ -295,6 +471,11 @@ def main():
     launches = eng.launches() - launches0
     ms = dist_max(dist, ms_local)
     value = n_gpus * B * K / (ms * 1e-3)
+
+    collect_ok = None
+    if collect_fn is not None:
+        step(0)
+        collect_ok = verify_collect(a1mpc, eng, dist, n_gpus, rank, B, dev[0], collect_buf)
 
     # ---- per-step latency distribution (p50 solve us), separate pass with a sync per step ----
     lat = []
@@ -339,6 +520,15 @@ def main():
     e2e_value = n_gpus * B * Ke / (max(e2e_ms, 1e3 * 0) * 1e-3)
     clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
 
+    # ---- sub-records: the other BASELINE configs at their stated sizes (outside the headline's timed region) ----
+    sub = {}
+    if not args.no_subrecords and B == 1024 and N == 10:
+        if n_gpus > 1:
+            sub["config5"] = subrecord_config5(a1mpc, eng, dist, n_gpus, rank, args.collect if collect_fn is not None else None)
+        elif rank == 0:
+            sub["config3"] = subrecord_config3(a1mpc, local)
+            sub["config4"] = subrecord_config4(a1mpc, local)
+
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (most device time among the class kernels) ----
@@ -362,15 +552,17 @@ def main():
             it_by_class[ns] = float(np.mean(iters0[m] % 100 + iters0[m] // 100))   # factorizations per QP
     fl_alg, fl_exec = algorithmic_flops(N, {dom: dom_qps}, it_by_class)
     traffic = None
+    traffic_src = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        ent = tj.get("solve_kernel<NS=%d,N=%d>@%d" % (dom, N, B))
+        ent = tj.get("kernels", {}).get("solve_kernel<NS=%d,N=%d>@%d" % (dom, N, B))
         if ent:
             traffic = ent["dram_bytes_read"] + ent["dram_bytes_write"]
+            traffic_src = "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch of %s (%s; tools/make_traffic_json.py)" % (ent["ncu_kernel_name"], tj.get("source"))
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "solve_kernel<NS=%d,N=%d>" % (dom, N), "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak, "traffic": traffic, "traffic_source": "ncu dram__bytes_read+write of one launch, profiles/traffic.json" if traffic else None,
+                "frac": achieved_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_qp": ALG_BYTES_PER_QP, "qps_per_launch": dom_qps, "kernel_ms": dom_ms,
                 "note": "the path is fp64-pipe/latency bound (SURVEY 8d: ~1e4 FLOP/B), so the HBM fraction is small by construction; see roofline_fp64"}
@@ -383,19 +575,20 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         from oracle import oracle_py as O
-        nthreads = O.hardware_threads()
-        v, S, sec = cpu_reference_rate(dict(horizon=N), args.config_id, nthreads, args.cpu_seconds, O, a1mpc)
-        v1, S1, sec1 = cpu_reference_rate(dict(horizon=N), args.config_id, 1, 2.0, O, a1mpc)
-        cpu = {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port",
+        nthreads, core_info = O.effective_cores()
+        v, S, sec = cpu_reference_rate(dict(horizon=N), args.config_id, nthreads, args.cpu_seconds, O)
+        v1, S1, sec1 = cpu_reference_rate(dict(horizon=N), args.config_id, 1, 2.0, O)
+        cpu = {"value": v, "unit": UNIT, "cores": nthreads, "cores_detail": core_info, "kind": "port",
                "sample": "%d synthetic QPs (same generator/distribution as the step batch) in %.1f s; dense ConvexMpc build + OSQP-algorithm restatement at OSQP defaults (eps 1e-3), cold start" % (S, sec),
                "single_thread_value": v1}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "trot gait convex MPC, horizon N=%d, batch %d per GPU, fp64 (BASELINE configs[1]%s)" % (N, B, "" if (B == 1024 and N == 10) else " variant"),
                        "horizon": N, "batch_per_gpu": B, "global_batch": B * n_gpus, "generator": "a1mpc_gen_states config_id=%d" % args.config_id,
-                       "cache": "inputs rotate through a ring of %d distinct batches = %.0f MB > L2 (126 MB)" % (ring, ring_bytes / 1e6),
+                       "cache": "inputs rotate through a ring of %d distinct batches = %.0f MB %s L2 (126 MB)" % (ring, ring_bytes / 1e6, ">" if ring_bytes > L2_BYTES else "< (NOT larger than)"),
                        "stance_feet_histogram": hist,
-                       "final_collect": ("ncclAllGather of [12][B] forces per step" if gather is not None else ("none" if n_gpus == 1 or args.no_gather else "unavailable: %s" % gather_err))},
+                       "final_collect_verified": collect_ok,
+                       "final_collect": (collect_desc if collect_fn is not None else ("none" if n_gpus == 1 or args.no_gather else "unavailable: %s" % collect_err))},
             "p50_solve_us": float(np.percentile(lat, 50)), "p99_solve_us": float(np.percentile(lat, 99)),
             "p50_solve_us_per_qp": float(np.percentile(lat, 50)) / B,
             "status_histogram": {int(k): int(v) for k, v in zip(*np.unique(status0, return_counts=True))},
@@ -404,6 +597,7 @@ def main():
             "gpu_launches": launches,
             "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu, "clocks": clocks,
             "class_kernel_ms_per_step": {int(i + 1): float(class_ms[i] / max(ncalls, 1)) for i in range(4)}}
+    line.update(sub)
     print(json.dumps(line), flush=True)
 
 

@@ -175,6 +175,11 @@ int  a1mpc_build_qp_batch(a1mpc_handle* h, int B, const a1mpc_inputs* in,
  *   x0 [B][13] (mpc_states), x_d [B][13N] (mpc_states_d);  outputs as above. */
 int  a1mpc_qp_mats_batch(a1mpc_handle* h, int B, const double* A_d, const double* B_d_list,
                          const double* x0, const double* x_d, double* H, double* g);
+/* The same call with the intermediate public members of ConvexMpc as well (ConvexMpc.h:77-78, ConvexMpc.cpp:181-202):
+ *   A_qp [B][13N][13] (rows 13i.. = A_d^(i+1)),  B_qp [B][13N][12N] (block (i,j) = A_d^(i-j) B_d[j], j <= i, zero above).
+ * Any output may be NULL (at least one must not be). */
+int  a1mpc_qp_rollout_batch(a1mpc_handle* h, int B, const double* A_d, const double* B_d_list,
+                            const double* x0, const double* x_d, double* A_qp, double* B_qp, double* H, double* g);
 
 /* OsqpEigen::Solver replacement for the MPC QP (A1RobotControl.cpp:522-555):
  *   min 1/2 u'Hu + g'u  s.t. the friction pyramid of ConvexMpc.cpp:46-58 with the contact
@@ -293,6 +298,26 @@ int  a1mpc_nccl_init(a1mpc_handle* h, int nranks, int rank, const void* unique_i
  * the handle's collect stream after everything enqueued so far and overlaps later solves; a1mpc_sync and a1mpc_event_record
  * wait for it.  Do not overwrite f_local / read f_all before one of them. */
 int  a1mpc_allgather_forces(a1mpc_handle* h, const double* f_local, double* f_all, int B_local);
+
+/* ---- fused final collect (SURVEY 2.3 last row / 8e): the solve kernels store the forces into every GPU's gathered buffer -------
+ * One process per GPU.  Each rank allocates its gathered buffer f_all [nranks][12][B_local] with a1mpc_peer_gather_create, which
+ * returns a 64-byte CUDA IPC handle; the ranks exchange the handles (any transport: the caller's MPI / torch.distributed / files)
+ * and map each other's buffers with a1mpc_peer_gather_connect.  From then on every a1mpc_solve_batch / _warm call with device
+ * pointers and B == B_local ALSO stores the 12 forces of every QP, straight from the solve kernels' epilogue, into block [rank] of
+ * every rank's buffer (plain peer stores over NVLink / NVSwitch -- no collective call, no extra pass over the data) and then
+ * publishes the call's sequence number to every rank.  a1mpc_peer_gather_wait enqueues, on the handle's stream, a wait until the
+ * forces of this rank's latest call number have arrived from ALL ranks (the ranks must make the same sequence of calls).
+ * Semantics: "latest value" -- a rank that runs ahead overwrites its block with its next call's forces; callers that must consume
+ * call k everywhere before any rank starts call k+1 add their own barrier.  precision 32: the buffer holds float.
+ * A peer that never arrives is reported by a1mpc_peer_gather_status (0 = fine, r+1 = rank r timed out after ~2 s) instead of hanging.
+ * Needs peer access between the GPUs (same NVLink domain) and CUDA IPC between the processes; A1MPC_ECUDA otherwise -- the NCCL
+ * all-gather above remains available as the portable path. */
+int  a1mpc_peer_gather_create(a1mpc_handle* h, int nranks, int rank, int B_local, void* ipc_handle64);
+int  a1mpc_peer_gather_connect(a1mpc_handle* h, const void* all_handles /* nranks x 64 bytes, rank order */);
+int  a1mpc_peer_gather_buffer(a1mpc_handle* h, double** f_all);
+int  a1mpc_peer_gather_wait(a1mpc_handle* h);
+int  a1mpc_peer_gather_status(a1mpc_handle* h, int* timed_out_rank_plus_1);
+int  a1mpc_peer_gather_destroy(a1mpc_handle* h);
 
 /* ---- synthetic workload generator, host-side, deterministic ------------------- */
 /* Fills host SoA arrays (ld = B) with the trot-gait state distribution of the benchmark.

@@ -228,6 +228,47 @@ def hardware_threads():
     return int(lib().oracle_hardware_threads())
 
 
+def effective_cores():
+    """host cores this process may actually use: min(scheduler affinity, cgroup CPU quota).  std::thread::hardware_concurrency()
+    (hardware_threads) reports the machine's logical CPUs even inside a container limited to a fraction of them -- the 1-GPU
+    lease of round 1 said 128 and delivered 11."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:          # cgroup v2: "<quota> <period>" or "max <period>"
+            q, per = fh.read().split()
+            if q != "max":
+                quota = float(q) / float(per)
+    except Exception:
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as fq, open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as fp:
+                q, per = float(fq.read()), float(fp.read())
+                if q > 0:
+                    quota = q / per
+        except Exception:
+            pass
+    eff = n if quota is None else max(1, min(n, int(np.ceil(quota))))
+    return eff, dict(affinity=n, cgroup_quota=quota, hardware_concurrency=hardware_threads())
+
+
+_GEN = None
+
+
+def gen_states(B, config_id=2, stream=0):
+    """the benchmark's synthetic states from oracle/liba1mpc_gen.so (csrc/a1mpc_gen.cpp compiled host-only): identical to
+    a1mpc.gen_states, without loading the CUDA library"""
+    global _GEN
+    if _GEN is None:
+        so = os.path.join(_HERE, "liba1mpc_gen.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", _HERE, "-s"])
+        _GEN = C.CDLL(so)
+    x0 = np.zeros((12, B)); rot = np.zeros((9, B)); foot = np.zeros((12, B)); ref = np.zeros((9, B)); contact = np.zeros(B, dtype=np.uint32)
+    rc = _GEN.a1mpc_gen_states(int(config_id), C.c_uint64(int(stream)), int(B), _ptr(x0), _ptr(rot), _ptr(foot), _ptr(ref), _ptr(contact))
+    assert rc == 0
+    return dict(x0=x0, rot=rot, foot=foot, ref=ref, contact=contact)
+
+
 def test_mpc_fixture():
     """The hand-built state of the reference's only standalone driver (test/test_mpc.cpp:15-91)."""
     cfg = make_config(horizon=10, mass=15.0, q=(1, 1, 1, 0, 0, 50, 0, 0, 1, 1, 1, 1, 0), r=(1e-6,) * 12)

@@ -72,5 +72,34 @@ int main() {
     for (int leg : {1, 3}) err = std::fmax(err, std::fabs(mpc_solver.solution[3 * leg + a]) + std::fabs(grf[0][a * 4 + leg]));
   }
   std::printf("max |f - f*| = %.3e N, status %d %d\n", err, (int)mpc_solver.status[0], (int)status[2]);
-  return (err <= 1e-4 && mpc_solver.status[0] == 0 && status[2] == 0) ? 0 : 1;
+  // ---- the other public members of the reference class (ConvexMpc.h:45-88) and compute_grf's state write-backs ----
+  // A_qp block i = A_d^(i+1): for this fixture A_d = I + dt A_c with yaw = 0, so the position/velocity coupling grows linearly
+  double merr = 0;
+  for (int i = 0; i < N; ++i) {
+    merr = std::fmax(merr, std::fabs(mpc_solver.A_qp[(13 * i + 3) * 13 + 9] - dt * (i + 1)));      // d pos_x / d vel_x
+    merr = std::fmax(merr, std::fabs(mpc_solver.A_qp[(13 * i + 11) * 13 + 12] - dt * (i + 1)));     // gravity state into v_z
+    // B_qp block (i, i) is B_d itself, blocks above the diagonal are zero
+    for (int r = 0; r < 13; ++r)
+      for (int c = 0; c < 12; ++c) {
+        merr = std::fmax(merr, std::fabs(mpc_solver.B_qp[(size_t)(13 * i + r) * 12 * N + 12 * i + c] - mpc_solver.B_mat_d[r * 12 + c]));
+        if (i + 1 < N) merr = std::fmax(merr, std::fabs(mpc_solver.B_qp[(size_t)(13 * i + r) * 12 * N + 12 * (i + 1) + c]));
+      }
+  }
+  // H = B_qp' Q B_qp + R recomputed on the host from the exposed members must reproduce the hessian member
+  {
+    const int n = 12 * N, m = 13 * N;
+    double hmax = 0;
+    for (double v : mpc_solver.hessian) hmax = std::fmax(hmax, std::fabs(v));
+    for (int a = 0; a < n; a += 7)
+      for (int b = 0; b < n; b += 5) {
+        double h = (a == b) ? mpc_solver.R[a] : 0.0;
+        for (int k = 0; k < m; ++k) h += mpc_solver.B_qp[(size_t)k * n + a] * mpc_solver.Q[k] * mpc_solver.B_qp[(size_t)k * n + b];
+        merr = std::fmax(merr, std::fabs(h - mpc_solver.hessian[(size_t)a * n + b]) / hmax);
+      }
+  }
+  merr = std::fmax(merr, std::fabs(mpc_solver.linear_constraints[(size_t)(5 * 7 + 1) * 12 * N + 3 * 7 + 2] + 0.3));   // row 1 of foot-step 7: [1 0 -mu]
+  merr = std::fmax(merr, std::fabs(states[1].mpc_states[5] - 0.15) + std::fabs(states[1].mpc_states[12] + 9.8));
+  merr = std::fmax(merr, states[1].mpc_states_d.size() == 13u * N ? std::fabs(states[1].mpc_states_d[13 * 9 + 5] - 0.15) : 1.0);
+  std::printf("public members / write-backs: max deviation %.3e\n", merr);
+  return (err <= 1e-4 && merr <= 1e-9 && mpc_solver.status[0] == 0 && status[2] == 0) ? 0 : 1;
 }

@@ -42,7 +42,7 @@ def test_gpu_build_matches_reference_built_qp(built):
         H, g, lb, ub = eng.build_qp(_states(G, sel))
         for k, i in enumerate(sel):
             assert np.array_equal(lb[k], G["mpc_lb"][i]) and np.array_equal(ub[k], G["mpc_ub"][i])
-            assert np.array_equal(H[k], H[k].T)
+            assert np.abs(H[k] - H[k].T).max() <= 1e-15 * np.abs(H[k]).max()   # symmetric to rounding (the two triangles are summed in different orders)
             if i < G["mpc_Hfull_triu"].shape[0]:
                 worst["H"] = max(worst["H"], _relerr(H[k][IU], G["mpc_Hfull_triu"][i]))
             worst["HV"] = max(worst["HV"], _relerr(H[k] @ V, G["mpc_HV"][i]), _relerr(np.diag(H[k]), G["mpc_Hdiag"][i]))
