@@ -79,19 +79,22 @@ void fused_launch_n10(int ns, const ClassLaunch& c, cudaStream_t st, int B, cons
 #ifndef A1MPC_N20_WPC2
 #define A1MPC_N20_WPC2 3   // one CTA of three warps with the rendezvous instead of three independent one-warp CTAs: trot N = 20 B = 16384
 #endif                     // 0.55 -> 0.79 M QPs/s on a B200 (profiles/r02b_*.txt): one instruction-cache fill serves the three warps
+#ifndef A1MPC_N20_WPC34
+#define A1MPC_N20_WPC34 2  // wrench classes at N = 20: 106.5 KB per warp since B_k is no longer stored -> two warps per SM instead of one
+#endif
 cudaError_t fused_setup_n20(int sm_count, ClassLaunch (&cls)[5]) {
   cudaError_t e;
   if ((e = setup_one<1, 20, A1MPC_N20_WPC1, 0>(sm_count, cls[1])) != cudaSuccess) return e;
   if ((e = setup_one<2, 20, A1MPC_N20_WPC2, 0>(sm_count, cls[2])) != cudaSuccess) return e;
-  if ((e = setup_one<3, 20, 1, 1>(sm_count, cls[3])) != cudaSuccess) return e;
-  if ((e = setup_one<4, 20, 1, 1>(sm_count, cls[4])) != cudaSuccess) return e;
+  if ((e = setup_one<3, 20, A1MPC_N20_WPC34, 1>(sm_count, cls[3])) != cudaSuccess) return e;
+  if ((e = setup_one<4, 20, A1MPC_N20_WPC34, 1>(sm_count, cls[4])) != cudaSuccess) return e;
   return cudaSuccess;
 }
 void fused_launch_n20(int ns, const ClassLaunch& c, cudaStream_t st, int B, const DevParams& P, const double* rec, const int* count, const DevOutputs& out) {
   if (ns == 1) launch_one<1, 20, A1MPC_N20_WPC1, 0>(c, st, B, P, rec, count, out);
   if (ns == 2) launch_one<2, 20, A1MPC_N20_WPC2, 0>(c, st, B, P, rec, count, out);
-  if (ns == 3) launch_one<3, 20, 1, 1>(c, st, B, P, rec, count, out);
-  if (ns == 4) launch_one<4, 20, 1, 1>(c, st, B, P, rec, count, out);
+  if (ns == 3) launch_one<3, 20, A1MPC_N20_WPC34, 1>(c, st, B, P, rec, count, out);
+  if (ns == 4) launch_one<4, 20, A1MPC_N20_WPC34, 1>(c, st, B, P, rec, count, out);
 }
 #endif
 

@@ -531,6 +531,16 @@ def main():
 
     if rank != 0:
         return
+    # ---- the plugin-level call a user of the reference makes, with pageable memory (C++ shim, its own process) ----
+    plugin = None
+    exe = os.path.join(ROOT, "tests", "cpp", "bench_compute_grf")
+    if n_gpus == 1 and not args.no_subrecords and os.path.exists(exe):
+        try:
+            eng.sync()
+            r = subprocess.run([exe, str(B), "200", "5"], capture_output=True, text=True, timeout=120)
+            plugin = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:
+            plugin = {"unavailable": str(e)}
     # ---- roofline of the dominant kernel (most device time among the class kernels) ----
     ns_of = np.array([bin(int(c) & 15).count("1") for c in host[0]["contact"]])
     hist = {ns: int((ns_of == ns).sum()) for ns in range(5)}
@@ -598,6 +608,8 @@ def main():
             "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu, "clocks": clocks,
             "class_kernel_ms_per_step": {int(i + 1): float(class_ms[i] / max(ncalls, 1)) for i in range(4)}}
     line.update(sub)
+    if plugin is not None:
+        line["e2e_plugin_pageable"] = plugin
     print(json.dumps(line), flush=True)
 
 

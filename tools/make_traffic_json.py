@@ -15,16 +15,16 @@ import subprocess
 import sys
 
 ap = argparse.ArgumentParser()
-ap.add_argument("rep")
+ap.add_argument("rep", nargs="+", help="one or more .ncu-rep files, in launch order")
 ap.add_argument("--batches", required=True, help="batch size of every successive group of class launches, e.g. 1024,1024,32768,32768")
 ap.add_argument("--source", default="")
 ap.add_argument("--out", default=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json"))
 args = ap.parse_args()
-raw = subprocess.run(["ncu", "-i", args.rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(raw.splitlines()))
-hdr = rows[0]
-ix = {h: i for i, h in enumerate(hdr)}
-units = rows[1]
+reports = []
+for rep in args.rep:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rws = list(csv.reader(raw.splitlines()))
+    reports.append((rws[0], rws[1], rws[2:]))
 
 
 def to_bytes(v, unit):
@@ -33,23 +33,26 @@ def to_bytes(v, unit):
 
 
 batches = [int(b) for b in args.batches.split(",")]
-groups, seen = [], set()
-for r in rows[2:]:
-    name = r[ix["Kernel Name"]]
-    m = re.search(r"solve_kernel(?:_warm)?<(\d+), (\d+), (\d+), (\d+)(?:, (\d+))?>", name)
-    if not m:
-        continue
-    key = (int(m.group(1)), int(m.group(2)))
-    if not groups or key in seen:
-        groups.append([])
-        seen = set()
-    seen.add(key)
-    groups[-1].append((key, name, r))
+groups = []
+for hdr, units, rows in reports:
+    ix = {h: i for i, h in enumerate(hdr)}
+    seen = None
+    for r in rows:
+        name = r[ix["Kernel Name"]]
+        m = re.search(r"solve_kernel(?:_warm)?<(\d+), (\d+), (\d+), (\d+)(?:, (\d+))?>", name)
+        if not m:
+            continue
+        key = (int(m.group(1)), int(m.group(2)))
+        if seen is None or key in seen:
+            groups.append([])
+            seen = set()
+        seen.add(key)
+        groups[-1].append((key, name, r, ix, units))
 if len(groups) != len(batches):
     sys.exit("found %d groups of class launches, --batches names %d" % (len(groups), len(batches)))
-out = {"source": args.source or os.path.basename(args.rep), "tool": "tools/make_traffic_json.py", "kernels": {}}
+out = {"source": args.source or ", ".join(os.path.basename(r) for r in args.rep), "tool": "tools/make_traffic_json.py", "kernels": {}}
 for B, grp in zip(batches, groups):
-    for (ns, n), name, r in grp:
+    for (ns, n), name, r, ix, units in grp:
         rd = to_bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]])
         wr = to_bytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
         dur = float(r[ix["gpu__time_duration.sum"]].replace(",", ""))
