@@ -30,6 +30,8 @@ int fail(int code, const std::string& msg) {
 }  // namespace
 
 extern "C" void a1mpc_internal_nccl_destroy(void* comm);   // a1mpc_nccl.cpp
+extern "C" void* a1mpc_internal_gather_begin(a1mpc_handle* h);
+extern "C" void a1mpc_internal_gather_end(a1mpc_handle* h);
 
 struct a1mpc_handle {
   int device = 0;
@@ -1091,9 +1093,45 @@ int a1mpc_peer_gather_wait(a1mpc_handle* h) {
   if (!pg.connected) return fail(A1MPC_EINVAL, "a1mpc_peer_gather_connect first");
   CK(cudaSetDevice(h->device));
   int* err = (int*)((char*)pg.local + (size_t)pg.nranks * 12 * pg.B * 8 + (size_t)MAX_PEERS * 8);
-  peer_wait_kernel<<<1, 32, 0, h->stream>>>(pg.flags[pg.rank], pg.nranks, pg.step, (long long)4e9 /* ~2 s */, err);
-  h->launches++;
-  CK(cudaGetLastError());
+  // like the NCCL collect, the wait runs on the collect stream, forked after everything enqueued so far (this rank's signal included):
+  // the next solve is not held back by a slower peer; a1mpc_sync / a1mpc_event_record join it.  (Measured with the wait on the
+  // compute stream, 2 x B200, B = 1024: 0.456 ms per step against 0.414 without any collect -- every step then ends in lock-step with
+  // the slowest rank; profiles/r02_notes.md.)
+  cudaStream_t gs = (cudaStream_t)a1mpc_internal_gather_begin(h);
+  if (!gs) return fail(A1MPC_ECUDA, "could not create the collect stream");
+  // Preferred: stream memory operations (cuStreamWaitValue64, >=): the wait is done by the GPU's front end and occupies no SM.  A
+  // spinning wait KERNEL sits on one SM for most of every step once the compute stream runs ahead, and since the persistent solve
+  // kernels split their queue statically, one perturbed SM stretches the whole launch: measured +0.67 ms per 6.1 ms step at
+  // 2 x 32768 QPs (profiles/r02_notes.md).  The kernel (polling every 5 us, ~2 s cap) remains as the fallback.
+  typedef int (*wait_value_fn)(cudaStream_t, unsigned long long, unsigned long long, unsigned int);
+  static wait_value_fn wait_value = nullptr;
+  static bool looked_up = false;
+  if (!looked_up) {
+    looked_up = true;
+    const char* ev = std::getenv("A1MPC_PEER_WAIT_KERNEL");
+    if (!(ev && ev[0] == '1')) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuStreamWaitValue64", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+        wait_value = (wait_value_fn)fn;
+      else
+        cudaGetLastError();
+    }
+  }
+  bool done = false;
+  if (wait_value) {
+    done = true;
+    for (int p = 0; p < pg.nranks && done; ++p)
+      if (wait_value(gs, (unsigned long long)(uintptr_t)(pg.flags[pg.rank] + p), pg.step, 0u /* CU_STREAM_WAIT_VALUE_GEQ */) != 0) done = false;
+    if (!done) { wait_value = nullptr; cudaGetLastError(); }   // not supported on this memory / driver: use the kernel from now on
+    else h->launches += 0;
+  }
+  if (!done) {
+    peer_wait_kernel<<<1, 32, 0, gs>>>(pg.flags[pg.rank], pg.nranks, pg.step, (long long)4e9 /* ~2 s */, err);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  a1mpc_internal_gather_end(h);
   return A1MPC_OK;
 }
 

@@ -15,7 +15,7 @@ __global__ void pack_kernel(DevInputs in, int B, double* __restrict__ rec, int c
   const uint32_t mask = in.contact[b] & 15u;
   const int ns = __popc(mask);
   if (ns == 0) {  // every foot is pinned to zero by fz in [0,0] (ConvexMpc.cpp:233,238)
-    for (int k = 0; k < 12; ++k) st_force(out, k, b, 0.0);
+    st_zero_forces(out, b);
     out.status[b] = A1MPC_STATUS_NO_CONTACT;
     if (out.iters) out.iters[b] = 0;
     if (out.u_full)
@@ -48,7 +48,7 @@ __global__ void pack_ext_kernel(DevInputs in, const uint32_t* __restrict__ sched
     else s1 |= m << (4 * (st - 16));
   }
   if (s0 == 0ull && s1 == 0ull) {
-    for (int k = 0; k < 12; ++k) st_force(out, k, b, 0.0);
+    st_zero_forces(out, b);
     out.status[b] = A1MPC_STATUS_NO_CONTACT;
     if (out.iters) out.iters[b] = 0;
     if (out.u_full)
@@ -95,7 +95,7 @@ __global__ void pack_ext2_kernel(DevInputs in, const uint32_t* __restrict__ sche
     else s1 |= m << (4 * (st - 16));
   }
   if (s0 == 0ull && s1 == 0ull) {
-    for (int k = 0; k < 12; ++k) st_force(out, k, b, 0.0);
+    st_zero_forces(out, b);
     out.status[b] = A1MPC_STATUS_NO_CONTACT;
     if (out.iters) out.iters[b] = 0;
     if (out.u_full)
@@ -133,7 +133,7 @@ __global__ void unsupported_kernel(const double* __restrict__ rec, const int* __
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= count[cls]) return;
   const int b = __double2loint(rec[(size_t)q * REC_DOUBLES + 42]);
-  for (int k = 0; k < 12; ++k) st_force(out, k, b, 0.0);
+  st_zero_forces(out, b);
   out.status[b] = A1MPC_STATUS_NUMERICAL;
   if (out.iters) out.iters[b] = 0;
   if (out.u_full)
@@ -272,7 +272,7 @@ __global__ void flush_kernel(double* buf, size_t n, double v) {
 
 // -------------------------------------------------------------------------------------------
 // fused final collect (a1mpc_peer_gather_*): step flags between the GPUs of one job.  The forces themselves are stored by the
-// solve kernels (st_force); these two tiny kernels order them: after the solve kernels of call number `step` have completed on
+// solve kernels (st_forces); these two tiny kernels order them: after the solve kernels of call number `step` have completed on
 // this GPU, lane p of peer_signal_kernel publishes `step` in slot [rank] of rank p's flag array (system-scope release: the
 // kernel boundary before it has already made the peer stores visible); peer_wait_kernel spins (system-scope acquire loads) until
 // every rank's slot of the LOCAL flag array has reached `step`, with a clock cap so that a dead peer cannot hang the GPU.
@@ -297,7 +297,7 @@ __global__ void peer_wait_kernel(const unsigned long long* __restrict__ local_fl
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(local_flags + lane) : "memory");
       if (v >= step) break;
       if (clock64() - t0 > max_cycles) { atomicExch(err, 1 + lane); break; }
-      __nanosleep(200);
+      __nanosleep(5000);   // 5 us: a tighter poll only perturbs the solve CTA that shares this SM
     }
   }
   __threadfence_system();

@@ -185,8 +185,8 @@ __global__ void __launch_bounds__(32 * WPC) solve_kernel_sched2(const __grid_con
       status = solve_qp<2, N, 0, SchedHess<N>, DirectLS<2, N, SchedHess<N>>>(c, hp, P, iters);
     }
     // outputs: legs in stance in the FIRST step carry a force; terrain frame -> world -> body (R^T)
+    double f[3] = {0.0, 0.0, 0.0};
     if (lane < 4) {
-      double f[3] = {0.0, 0.0, 0.0};
       int k0 = -1;
       if (legmap[0] == lane) k0 = 0;
       if (legmap[1] == lane) k0 = 1;
@@ -198,9 +198,8 @@ __global__ void __launch_bounds__(32 * WPC) solve_kernel_sched2(const __grid_con
 #pragma unroll
         for (int a = 0; a < 3; ++a) f[a] = c.rec[12 + a] * wx_ + c.rec[15 + a] * wy_ + c.rec[18 + a] * wz_;
       }
-#pragma unroll
-      for (int a = 0; a < 3; ++a) st_force(out, (3 * lane + a), b, f[a]);
     }
+    st_forces(out, b, f, lane, c.vtmp);
     if (lane == 0) {
       out.status[b] = status;
       if (out.iters) out.iters[b] = iters;

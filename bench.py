@@ -184,7 +184,7 @@ def setup_collect(a1mpc, eng, dist, n_gpus, rank, B, mode):
             except Exception as e:
                 err = str(e)
         if all(dist_allgather_obj(dist, ok, n_gpus)):
-            return ("fused: solve-kernel epilogue stores into every rank's buffer over NVLink (CUDA IPC peer memory) + per-step flag wait",
+            return ("fused: solve-kernel epilogue stores one 96-byte record per QP into every rank's buffer over NVLink (CUDA IPC peer memory) + step flags",
                     (lambda d: eng.peer_gather_wait()), None, eng.peer_gather_buffer())
         try:
             eng.peer_gather_destroy()
@@ -201,8 +201,15 @@ def setup_collect(a1mpc, eng, dist, n_gpus, rank, B, mode):
             if os.path.exists(cand):
                 os.environ.setdefault("A1MPC_NCCL_LIB", cand)
         if not getattr(eng, "_nccl_ready", False):
-            uid = a1mpc.nccl_unique_id() if rank == 0 else None
-            uid = dist_bcast_bytes(dist, uid, rank)
+            uid, uerr = None, None
+            if rank == 0:
+                try:
+                    uid = a1mpc.nccl_unique_id()
+                except Exception as e:      # still take part in the broadcast: the other ranks are waiting in it
+                    uerr = str(e)
+            uid, uerr = dist_bcast_bytes(dist, (uid, uerr), rank)
+            if uid is None:
+                raise RuntimeError(uerr)
             eng.nccl_init(n_gpus, rank, uid)
             eng._nccl_ready = True
         gbuf = eng.dalloc(n_gpus * 12 * B * 8)
@@ -211,17 +218,19 @@ def setup_collect(a1mpc, eng, dist, n_gpus, rank, B, mode):
         return "unavailable", None, "%s; nccl: %s" % (err, e), None
 
 
-def verify_collect(a1mpc, eng, dist, n_gpus, rank, B, d, gbuf):
+def verify_collect(a1mpc, eng, dist, n_gpus, rank, B, d, gbuf, qp_major):
     """after one more step + wait: block [p] of every rank's gathered buffer must be rank p's own f_body, bit for bit"""
     eng.sync()
     dist_barrier(dist)
     f, _ = d.download()
     mine = int(np.ascontiguousarray(f).view(np.uint64).sum(dtype=np.uint64))
     sums = dist_allgather_obj(dist, mine, n_gpus)
-    g = np.zeros((n_gpus, 12, B), dtype=f.dtype)
+    g = np.zeros((n_gpus, 12 * B), dtype=f.dtype)
     a1mpc._check(a1mpc.lib().a1mpc_memcpy_d2h(eng.h, g.ctypes.data, gbuf, g.nbytes))
     eng.sync()
-    ok = all(int(np.ascontiguousarray(g[p]).view(np.uint64).sum(dtype=np.uint64)) == sums[p] for p in range(n_gpus)) and np.array_equal(g[rank], f)
+    # block [rank] is batch-major [12][B] from ncclAllGather, QP-major [B][12] from the fused peer stores
+    own = g[rank].reshape(12, B) if qp_major is False else g[rank].reshape(B, 12).T
+    ok = all(int(np.ascontiguousarray(g[p]).view(np.uint64).sum(dtype=np.uint64)) == sums[p] for p in range(n_gpus)) and np.array_equal(own, f)
     return bool(all(dist_allgather_obj(dist, bool(ok), n_gpus)))
 
 
@@ -331,7 +340,7 @@ def subrecord_config5(a1mpc, eng, dist, n_gpus, rank, collect_mode, K=30, W=3):
     verified = None
     if fn is not None:
         step(0)
-        verified = verify_collect(a1mpc, eng, dist, n_gpus, rank, B, dev[0], gbuf)
+        verified = verify_collect(a1mpc, eng, dist, n_gpus, rank, B, dev[0], gbuf, desc.startswith("fused"))
     rec = {"workload": "trot gait convex MPC, horizon N=10, batch 32768 per GPU = %d QPs per step, fp64 (BASELINE configs[4])" % (B * n_gpus),
            "value": n_gpus * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": K, "warmup": W, "dtype": "f64", "n_gpus": n_gpus,
            "final_collect": desc if fn is not None else ("none" if not collect_mode else "unavailable: %s" % err), "peer_wait_timeouts": peer_status, "final_collect_verified": verified,
@@ -475,7 +484,7 @@ def main():
     collect_ok = None
     if collect_fn is not None:
         step(0)
-        collect_ok = verify_collect(a1mpc, eng, dist, n_gpus, rank, B, dev[0], collect_buf)
+        collect_ok = verify_collect(a1mpc, eng, dist, n_gpus, rank, B, dev[0], collect_buf, collect_desc.startswith("fused"))
 
     # ---- per-step latency distribution (p50 solve us), separate pass with a sync per step ----
     lat = []

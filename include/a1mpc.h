@@ -300,16 +300,22 @@ int  a1mpc_nccl_init(a1mpc_handle* h, int nranks, int rank, const void* unique_i
 int  a1mpc_allgather_forces(a1mpc_handle* h, const double* f_local, double* f_all, int B_local);
 
 /* ---- fused final collect (SURVEY 2.3 last row / 8e): the solve kernels store the forces into every GPU's gathered buffer -------
- * One process per GPU.  Each rank allocates its gathered buffer f_all [nranks][12][B_local] with a1mpc_peer_gather_create, which
+ * One process per GPU.  Each rank allocates its gathered buffer f_all [nranks][B_local][12] (QP-major: the 12 body-frame forces of a
+ * robot are contiguous, leg-major -- NOT the batch-major layout of f_body / ncclAllGather) with a1mpc_peer_gather_create, which
  * returns a 64-byte CUDA IPC handle; the ranks exchange the handles (any transport: the caller's MPI / torch.distributed / files)
  * and map each other's buffers with a1mpc_peer_gather_connect.  From then on every a1mpc_solve_batch / _warm call with device
  * pointers and B == B_local ALSO stores the 12 forces of every QP, straight from the solve kernels' epilogue, into block [rank] of
- * every rank's buffer (plain peer stores over NVLink / NVSwitch -- no collective call, no extra pass over the data) and then
- * publishes the call's sequence number to every rank.  a1mpc_peer_gather_wait enqueues, on the handle's stream, a wait until the
- * forces of this rank's latest call number have arrived from ALL ranks (the ranks must make the same sequence of calls).
+ * every rank's buffer (one contiguous 96-byte peer store per QP and rank over NVLink / NVSwitch -- no collective call, no extra pass
+ * over the data) and then
+ * publishes the call's sequence number to every rank.  a1mpc_peer_gather_wait enqueues, on the handle's collect stream (forked after
+ * everything enqueued so far, so that later solves are not held back by a slower peer; a1mpc_sync and a1mpc_event_record join
+ * it, exactly like the NCCL collect), a wait until the forces of this rank's latest call number have arrived from ALL ranks
+ * (the ranks must make the same sequence of calls).
  * Semantics: "latest value" -- a rank that runs ahead overwrites its block with its next call's forces; callers that must consume
  * call k everywhere before any rank starts call k+1 add their own barrier.  precision 32: the buffer holds float.
- * A peer that never arrives is reported by a1mpc_peer_gather_status (0 = fine, r+1 = rank r timed out after ~2 s) instead of hanging.
+ * The wait itself is a stream memory operation (cuStreamWaitValue64 on this rank's flag array: no SM is occupied); where the driver
+ * refuses it, or with A1MPC_PEER_WAIT_KERNEL=1, a one-warp polling kernel with a ~2 s cap is used instead, and a peer that never
+ * arrives is then reported by a1mpc_peer_gather_status (0 = fine, r+1 = rank r timed out) instead of hanging the stream.
  * Needs peer access between the GPUs (same NVLink domain) and CUDA IPC between the processes; A1MPC_ECUDA otherwise -- the NCCL
  * all-gather above remains available as the portable path. */
 int  a1mpc_peer_gather_create(a1mpc_handle* h, int nranks, int rank, int B_local, void* ipc_handle64);

@@ -198,6 +198,11 @@ using std::sqrt;
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline double __drcp_rn(double x) { return 1.0 / x; }
 inline double __dsqrt_rn(double x) { return std::sqrt(x); }
+// vector types used by the fused-collect store path of the device code (never executed by the emulator: npeer == 0)
+struct float2 { float x, y; };
+struct double2 { double x, y; };
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline int __double2hiint(double x) { return (int)(uint32_t)(a1emu::d2u(x) >> 32); }
 inline int __double2loint(double x) { return (int)(uint32_t)(a1emu::d2u(x) & 0xffffffffull); }
 inline long long __double_as_longlong(double x) { return (long long)a1emu::d2u(x); }

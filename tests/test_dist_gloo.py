@@ -25,6 +25,25 @@ out = [torch.zeros_like(t) for _ in range(2)]
 dist.all_gather(out, t)
 assert not torch.equal(out[0], out[1])                   # shards differ
 assert torch.equal(out[rank], t)
+# the collect set-up must take the same branch on every rank and never leave a rank waiting in a collective: rank 1 cannot create
+# its peer buffer, rank 0 cannot produce an NCCL id -> both end with "unavailable", no hang
+class FakeEng:
+    def peer_gather_create(self, n, r, B):
+        if r == 1:
+            raise RuntimeError("no peer access (test)")
+        return b"h" * 64
+    def peer_gather_connect(self, hs): pass
+    def peer_gather_destroy(self): pass
+    def peer_gather_buffer(self): return None
+    def nccl_init(self, *a): raise RuntimeError("nccl_init must not be reached")
+class FakeA1:
+    @staticmethod
+    def nccl_unique_id(): raise RuntimeError("no NCCL (test)")
+desc, fn, err, buf = bench.setup_collect(FakeA1, FakeEng(), dist, 2, rank, 64, "auto")
+assert desc == "unavailable" and fn is None and "no NCCL (test)" in err, (desc, err)
+desc, fn, err, buf = bench.setup_collect(FakeA1, FakeEng(), dist, 2, rank, 64, "peer")
+assert desc == "unavailable" and fn is None
+assert bench.dist_allgather_obj(dist, rank * 7, 2) == [0, 7]
 bench.dist_barrier(dist)
 sys.stdout.write("RANK_OK " + str(rank) + "\n"); sys.stdout.flush()    # one write per rank: the two ranks share a pipe
 '''

@@ -1,0 +1,15 @@
+#!/bin/bash
+# round 2, seventh gpurun call (multi-GPU): the fused collect with one contiguous 96-byte record per QP and peer, wait on the collect stream
+mkdir -p gpurun_out; O=gpurun_out
+NG=${NG:-2}
+run() { n=$1; name=$2; shift; shift; timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 296$n$n bench.py --gpus $n --steps 400 --warmup 10 --no-cpu-baseline "$@" > $O/r02g_${n}_$name.json 2> $O/r02g_${n}_$name.err; echo "== $n GPUs $name rc=$?"; python - <<PY
+import json
+try:
+    d=json.loads(open("$O/r02g_${n}_$name.json").read().strip().splitlines()[-1]); c=d.get("config5",{})
+    print("value %.3f M ms %.4f p50 %.1f collect %s verified %s | config5 %.2f M %.3f ms verified %s timeouts %s" % (d["value"]/1e6,d["ms_per_step"],d["p50_solve_us"],d["config"]["final_collect"][:24],d["config"]["final_collect_verified"],c.get("value",0)/1e6,c.get("ms_per_step",0),c.get("final_collect_verified"),c.get("peer_wait_timeouts")))
+except Exception as e:
+    print("no line:", e)
+PY
+tail -2 $O/r02g_${n}_$name.err; }
+run $NG peer
+run $NG nccl --collect nccl
