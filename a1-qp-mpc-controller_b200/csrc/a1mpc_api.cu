@@ -7,6 +7,7 @@
 #include <vector>
 
 #include <algorithm>
+#include <initializer_list>
 
 #include "a1mpc_internal.h"
 #include "a1mpc_misc.cuh"
@@ -155,6 +156,14 @@ bool is_device_ptr(const void* p) {
     return false;
   }
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// true when the non-NULL pointers do not all live on the same side as `dev` says (a host pointer dereferenced by a kernel is a sticky
+// fault for the whole CUDA context, so every entry point classifies every array it is given)
+bool mixed_sides(bool dev, std::initializer_list<const void*> ptrs) {
+  for (const void* q : ptrs)
+    if (q && is_device_ptr(q) != dev) return true;
+  return false;
 }
 
 // enqueue the fused path on device-resident SoA data
@@ -491,6 +500,7 @@ int a1mpc_build_qp_batch(a1mpc_handle* h, int B, const a1mpc_inputs* in, double*
   CK(cudaSetDevice(h->device));
   const int N = h->cfg.horizon, n = 12 * N, m = 20 * N;
   const bool dev = is_device_ptr(in->x0);
+  if (mixed_sides(dev, {in->rot, in->foot, in->ref, in->contact, H, g, lb, ub})) return fail(A1MPC_EINVAL, "inputs and outputs must be all-host or all-device");
   int rc;
   DevInputs di{in->x0, in->rot, in->foot, in->ref, in->contact, in->ld};
   double *dH = H, *dg = g, *dlb = lb, *dub = ub;
@@ -589,6 +599,7 @@ int a1mpc_solve_dense_batch(a1mpc_handle* h, int B, const double* H, const doubl
   CK(cudaSetDevice(h->device));
   const int N = h->cfg.horizon, n = 12 * N;
   const bool dev = is_device_ptr(H);
+  if (mixed_sides(dev, {g, contact, u, status})) return fail(A1MPC_EINVAL, "inputs and outputs must be all-host or all-device");
   const size_t Bs = (size_t)B;
   const double *dH = H, *dg = g;
   const uint32_t* dc = contact;
@@ -628,6 +639,7 @@ int a1mpc_grf_qp_batch(a1mpc_handle* h, int B, const double* root_acc, const dou
   if (B <= 0) return fail(A1MPC_EINVAL, "B must be positive");
   CK(cudaSetDevice(h->device));
   const bool dev = is_device_ptr(root_acc);
+  if (mixed_sides(dev, {rot_z, rot, foot, contact, f_body, status})) return fail(A1MPC_EINVAL, "inputs and outputs must be all-host or all-device");
   const size_t Bs = (size_t)B;
   const double *da = root_acc, *drz = rot_z, *dr = rot, *dfo = foot;
   const uint32_t* dc = contact;
@@ -667,6 +679,8 @@ int a1mpc_joint_torques_batch(a1mpc_handle* h, int B, const double* f_grf, const
   if (B <= 0) return fail(A1MPC_EINVAL, "B must be positive");
   CK(cudaSetDevice(h->device));
   const bool dev = is_device_ptr(f_grf);
+  if (mixed_sides(dev, {f_kin, jac, contact, tau})) return fail(A1MPC_EINVAL, "batch arrays must be all-host or all-device (km_foot, torques_gravity: always host)");
+  if (is_device_ptr(km_foot) || is_device_ptr(torques_gravity)) return fail(A1MPC_EINVAL, "km_foot and torques_gravity are host arrays (batch-uniform parameters)");
   const size_t Bs = (size_t)B;
   TorqueParams P;
   for (int i = 0; i < 3; ++i) P.km[i] = km_foot[i];

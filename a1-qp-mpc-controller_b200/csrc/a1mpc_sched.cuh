@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(32 * WPC) solve_kernel_sched2(const __grid_con
       int k0 = -1;
       if (legmap[0] == lane) k0 = 0;
       if (legmap[1] == lane) k0 = 1;
-      if (k0 >= 0) {
+      if (k0 >= 0 && !bad) {   // bad inputs: zero forces, nothing is multiplied with the poisoned record
         const double ux = c.vy[3 * k0] * FSCALE, uy = c.vy[3 * k0 + 1] * FSCALE, uz = c.vy[3 * k0 + 2] * FSCALE;
         double e0[3], e1[3], e2[3];
         terrain_col(c.rec + 46 + 3 * lane, 0, e0); terrain_col(c.rec + 46 + 3 * lane, 1, e1); terrain_col(c.rec + 46 + 3 * lane, 2, e2);
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(32 * WPC) solve_kernel_sched2(const __grid_con
         int k = -1;
         if (legmap[2 * st] == leg) k = 2 * st;
         if (legmap[2 * st + 1] == leg) k = 2 * st + 1;
-        if (k >= 0) {
+        if (k >= 0 && !bad) {
           double col[3], acc = 0.0;
 #pragma unroll
           for (int bb = 0; bb < 3; ++bb) { terrain_col(c.rec + 46 + 3 * leg, bb, col); acc = fma(col[a], c.vy[3 * k + bb], acc); }
