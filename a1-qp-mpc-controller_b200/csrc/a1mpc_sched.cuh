@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(32 * WPC) solve_kernel_sched2(const __grid_con
   int* legmap = reinterpret_cast<int*>(xs + SG::X_LEG);
   SchedHess<N> hp;
   hp.legmap = legmap; hp.vinf = xs + SG::X_VIN; hp.voutf = xs + SG::X_VOUT;
-  hp.cf.lane = lane; hp.cf.rec = c.rec; hp.cf.L = c.L; hp.cf.T0 = c.T0; hp.cf.T1 = c.T1;
+  hp.cf.lane = lane; hp.cf.tid = lane; hp.cf.wit = 0; hp.cf.barid = 0; hp.cf.rec = c.rec; hp.cf.L = c.L; hp.cf.T0 = c.T0; hp.cf.T1 = c.T1;
   hp.cf.g = xs + SG::X_G; hp.cf.G0 = xs + SG::X_G0; hp.cf.G1 = xs + SG::X_G1; hp.cf.R2 = xs + SG::X_R2;
   hp.cf.vp0 = xs + SG::X_VP0; hp.cf.vp1 = xs + SG::X_VP1;
   hp.cf.vu = hp.cf.vrhs = hp.cf.vtmp = hp.cf.vy = nullptr; hp.cf.D = nullptr; hp.cf.zinfo = nullptr; hp.cf.exist = nullptr;

@@ -17,7 +17,7 @@ static cudaError_t setup_n(int sm_count, ClassLaunch& c) {
   cudaError_t e = cudaFuncSetAttribute(solve_kernel<4, N, WPC, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<4, N, WPC, 1, true>, 32 * WPC, c.smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<4, N, WPC, 1, true>, 32 * WPC * Geo<4, N, 1>::TW, c.smem);
   if (e != cudaSuccess) return e;
   if (occ < 1) return cudaErrorLaunchOutOfResources;
   c.max_ctas = occ * sm_count;
@@ -31,8 +31,8 @@ void ext_launch(int horizon, const ClassLaunch& c, cudaStream_t st, int B, const
   int grid = (B + c.wpc - 1) / c.wpc;
   if (grid > c.max_ctas) grid = c.max_ctas;
   if (grid < 1) grid = 1;
-  if (horizon == 10) solve_kernel<4, 10, A1MPC_WPC34, 1, true><<<grid, 32 * A1MPC_WPC34, c.smem, st>>>(P, rec, count, out);
-  else solve_kernel<4, 20, 1, 1, true><<<grid, 32, c.smem, st>>>(P, rec, count, out);
+  if (horizon == 10) solve_kernel<4, 10, A1MPC_WPC34, 1, true><<<grid, 32 * A1MPC_WPC34 * Geo<4, 10, 1>::TW, c.smem, st>>>(P, rec, count, out);
+  else solve_kernel<4, 20, 1, 1, true><<<grid, 32 * Geo<4, 20, 1>::TW, c.smem, st>>>(P, rec, count, out);
 }
 
 cudaError_t sched2_setup(int sm_count, ClassLaunch& c) {

@@ -11,7 +11,7 @@ static cudaError_t setup_one(int sm_count, ClassLaunch& c) {
   cudaError_t e = cudaFuncSetAttribute(solve_kernel<NS, N, WPC, LSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<NS, N, WPC, LSM>, 32 * WPC, c.smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, solve_kernel<NS, N, WPC, LSM>, 32 * WPC * G::TW, c.smem);
   if (e != cudaSuccess) return e;
   if (occ < 1) return cudaErrorLaunchOutOfResources;
   c.max_ctas = occ * sm_count;
@@ -30,7 +30,7 @@ static void launch_one_warm(const ClassLaunch& c, cudaStream_t st, int B, const 
   int grid = (B + WPC - 1) / WPC;
   if (grid > c.max_ctas) grid = c.max_ctas;
   if (grid < 1) grid = 1;
-  solve_kernel_warm<NS, N, WPC, LSM><<<grid, 32 * WPC, c.smem, st>>>(P, rec, count, out, warm, shift);
+  solve_kernel_warm<NS, N, WPC, LSM><<<grid, 32 * WPC * Geo<NS, N, LSM>::TW, c.smem, st>>>(P, rec, count, out, warm, shift);
 }
 
 template <int NS, int N, int WPC, int LSM>
@@ -38,7 +38,7 @@ static void launch_one(const ClassLaunch& c, cudaStream_t st, int B, const DevPa
   int grid = (B + WPC - 1) / WPC;
   if (grid > c.max_ctas) grid = c.max_ctas;
   if (grid < 1) grid = 1;
-  solve_kernel<NS, N, WPC, LSM><<<grid, 32 * WPC, c.smem, st>>>(P, rec, count, out);
+  solve_kernel<NS, N, WPC, LSM><<<grid, 32 * WPC * Geo<NS, N, LSM>::TW, c.smem, st>>>(P, rec, count, out);
 }
 
 #ifndef A1MPC_HORIZON

@@ -48,7 +48,10 @@ struct Warp {
   uint64_t slot2[2][32];
 };
 
+struct NamedBarrier { unsigned gen = 0; int count = 0, acc_or = 0, acc_and = 1, res_or[2] = {0, 0}, res_and[2] = {1, 1}; };
+
 struct Block {
+  NamedBarrier nbar[16];
   int nthreads = 0;
   std::vector<Fiber> fib;
   std::vector<Warp> warps;
@@ -144,6 +147,26 @@ inline int __reduce_add_sync(unsigned, int v) {
   for (int l = 0; l < 32; ++l) s += (int)(uint32_t)w.slot[g & 1][l];
   return s;
 }
+namespace a1emu {
+// PTX bar.sync / bar.red.{or,and}.pred on named barrier `id` over `nthreads` threads: mode 0 barrier only, 1 returns the OR of the
+// predicates, 2 their AND.  Every participating thread must use the same mode (as on the GPU).
+inline int named_barrier(int id, int nthreads, int mode, int pred) {
+  NamedBarrier& nb = g_blk->nbar[id & 15];
+  const unsigned g = nb.gen;
+  nb.acc_or |= pred ? 1 : 0;
+  nb.acc_and &= pred ? 1 : 0;
+  if (++nb.count == nthreads) {
+    nb.res_or[g & 1] = nb.acc_or; nb.res_and[g & 1] = nb.acc_and;
+    nb.count = 0; nb.acc_or = 0; nb.acc_and = 1;
+    nb.gen = g + 1;
+    ++g_blk->progress;
+    ++g_blk->n_collectives;
+  } else {
+    while (nb.gen == g) yield_to_scheduler();
+  }
+  return mode == 1 ? nb.res_or[g & 1] : (mode == 2 ? nb.res_and[g & 1] : 0);
+}
+}  // namespace a1emu
 inline void __syncthreads() {
   a1emu::Block& b = *a1emu::g_blk;
   const unsigned g = b.bgen;

@@ -44,7 +44,7 @@ void run_class(const DevParams& P, const double* rec, const int* count, const De
       const int bx = next.fetch_add(1);
       if (bx >= grid) break;
       unsigned long nc = 0, nm = 0;
-      a1emu::run_block(a1emu::Dim3{(unsigned)bx, 0, 0}, a1emu::Dim3{(unsigned)grid, 1, 1}, 32 * WPC, G::smem_bytes(WPC), order_mode,
+      a1emu::run_block(a1emu::Dim3{(unsigned)bx, 0, 0}, a1emu::Dim3{(unsigned)grid, 1, 1}, 32 * WPC * G::TW, G::smem_bytes(WPC), order_mode,
                        [&]() {
                          if constexpr (!EXT) {
                            if (warm) { solve_kernel_warm<NS, N, WPC, LSM>(P, rec, count, out, warm, shift); return; }
