@@ -154,14 +154,14 @@ __device__ __forceinline__ void stance_map(int mask, int (&leg_of)[4]) {
 // One warp per QP: gather the stance sub-block of the caller's dense Hessian into shared memory
 // (scaled), solve, scatter u.
 template <int NS, int N>
-__global__ void __launch_bounds__(32) dense_solve_kernel(const __grid_constant__ DevParams P, const double* __restrict__ H,
+__global__ void __launch_bounds__(32 * Geo<NS, N>::TW) dense_solve_kernel(const __grid_constant__ DevParams P, const double* __restrict__ H,
                                                          const double* __restrict__ g, const uint32_t* __restrict__ contact,
                                                          const int* __restrict__ list, const int* __restrict__ count,
                                                          double* __restrict__ u, int32_t* __restrict__ status) {
   using G = Geo<NS, N>;
   using DG = DenseGeo<NS, N>;
   A1MPC_DYN_SMEM(smem);
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;   // one QP per CTA; the CTA is one team of G::TW warps
   Ctx<NS, N> c(smem + G::TAB_DOUBLES, smem, lane);
   double* Hs = smem + G::TAB_DOUBLES + G::WARP_DOUBLES;
   constexpr int n = 12 * N, NV = G::NV, A = G::A;
@@ -185,36 +185,37 @@ __global__ void __launch_bounds__(32) dense_solve_kernel(const __grid_constant__
     };
     double dmax = 0.0;
     bool bad = false;
-    for (int v = lane; v < NV; v += 32) {
+    for (int v = c.tid; v < NV; v += G::TS) {
       const int fv = full(v);
       const double d = Hb[(size_t)fv * n + fv];
       dmax = fmax(dmax, d);
       bad = bad || !(d > 0.0) || !(fabs(gb[fv]) < 1e300);
     }
-    dmax = warp_max(dmax);
-    bad = __any_sync(0xffffffffu, bad);
+    dmax = tmax(c, dmax);
+    bad = tany(c, bad);
     int st, iters = 0;
     if (bad) {
       st = A1MPC_STATUS_NUMERICAL;
-      for (int i = lane; i < G::NPAD; i += 32) c.vy[i] = 0.0;
-      __syncwarp();
+      for (int i = c.tid; i < G::NPAD; i += G::TS) c.vy[i] = 0.0;
+      tsync(c);
     } else {
       const double cs = dmax * FSCALE * FSCALE, hs = FSCALE * FSCALE / cs, gsc = FSCALE / cs;
-      for (int e = lane; e < NV * NV; e += 32) {
+      for (int e = c.tid; e < NV * NV; e += G::TS) {
         const int j = e / NV, i = e - j * NV;
         // symmetrise like OSQP does (osqp-eigen hands over the upper triangle only)
         const int fi = full(i), fj = full(j);
         const double v = (fi <= fj) ? Hb[(size_t)fi * n + fj] : Hb[(size_t)fj * n + fi];
         Hs[e] = v * hs;
       }
-      for (int v = lane; v < NV; v += 32) c.g[v] = gb[full(v)] * gsc;
-      __syncwarp();
-      fill_padding<NS, N, 0>(c);
+      for (int v = c.tid; v < NV; v += G::TS) c.g[v] = gb[full(v)] * gsc;
+      tsync(c);
+      if (c.wit == 0) fill_padding<NS, N, 0>(c);
+      if (G::TW > 1) tsync(c);
       DenseHess<NS, N> hp;
       hp.Hs = Hs;
       st = solve_qp<NS, N, 0, DenseHess<NS, N>, DirectLS<NS, N, DenseHess<NS, N>>>(c, hp, P, iters);
     }
-    for (int e = lane; e < n; e += 32) {
+    for (int e = c.tid; e < n; e += G::TS) {
       const int s = e / 12, r = e - 12 * s, leg = r / 3, a = r - 3 * leg;
       double v = 0.0;
 #pragma unroll
@@ -222,8 +223,8 @@ __global__ void __launch_bounds__(32) dense_solve_kernel(const __grid_constant__
         if (k < NS && leg_of[k] == leg && ((mask >> leg) & 1)) v = c.vy[s * A + 3 * k + a] * FSCALE;
       u[(size_t)b * n + e] = v;
     }
-    if (lane == 0) status[b] = st;
-    __syncwarp();
+    if (c.tid == 0) status[b] = st;
+    tsync(c);
   }
 }
 
@@ -383,7 +384,7 @@ template <int NS, int N>
 static void dense_launch_one(const DevParams& P, int sm_count, int B, const double* H, const double* g, const uint32_t* contact,
                              const int* list, const int* count, double* u, int32_t* status, cudaStream_t st) {
   int grid = B < sm_count * 4 ? B : sm_count * 4;
-  dense_solve_kernel<NS, N><<<grid, 32, DenseGeo<NS, N>::smem_bytes(), st>>>(P, H, g, contact, list + (size_t)(NS - 1) * B, count, u, status);
+  dense_solve_kernel<NS, N><<<grid, 32 * Geo<NS, N>::TW, DenseGeo<NS, N>::smem_bytes(), st>>>(P, H, g, contact, list + (size_t)(NS - 1) * B, count, u, status);
 }
 
 cudaError_t dense_solve_launch(const DevParams& P, int sm_count, int B, const double* H, const double* g, const uint32_t* contact, double* u,

@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(32 * WPC) solve_kernel_sched2(const __grid_con
                                                                 const int* __restrict__ count, DevOutputs out) {
   using G = Geo<2, N, 0>;
   using SG = SchedGeo<N>;
+  static_assert(G::TW == 1, "the compacted schedule kernel is written for one warp per QP (N = 10)");
   A1MPC_DYN_SMEM(smem);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   for (int e = threadIdx.x; e < N * N; e += blockDim.x) {

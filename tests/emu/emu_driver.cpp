@@ -86,7 +86,7 @@ void run_dense(const DevParams& P, int B, const double* H, const double* g, cons
                double* u, int32_t* status, int order_mode) {
   const int nq = count[NS];
   for (int bx = 0; bx < nq; ++bx)
-    a1emu::run_block(a1emu::Dim3{(unsigned)bx, 0, 0}, a1emu::Dim3{(unsigned)nq, 1, 1}, 32, DenseGeo<NS, N>::smem_bytes(), order_mode,
+    a1emu::run_block(a1emu::Dim3{(unsigned)bx, 0, 0}, a1emu::Dim3{(unsigned)nq, 1, 1}, 32 * Geo<NS, N>::TW, DenseGeo<NS, N>::smem_bytes(), order_mode,
                      [&]() { dense_solve_kernel<NS, N>(P, H, g, contact, list + (size_t)(NS - 1) * B, count, u, status); });
 }
 
@@ -113,11 +113,16 @@ extern "C" {
 // a1mpc_solve_dense_batch on the emulator (QP-major H [B,n,n], g [B,n], u [B,n]); N = 10 only
 int emu_solve_dense(const a1mpc_config* cfg, int B, const double* H, const double* g, const uint32_t* contact, double* u, int32_t* status,
                     int order_mode) {
-  if (cfg->horizon != 10) return -1;
+  if (cfg->horizon != 10 && cfg->horizon != 20) return -1;
   const DevParams P = make_params(cfg);
   std::vector<int> list((size_t)4 * B + 8, 0);
   int count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   classify(B, contact, list.data(), count, u, 12 * cfg->horizon, status);
+  if (cfg->horizon == 20) {   // a1mpc_dense.cu serves the direct classes at N = 20 (one or two stance feet)
+    run_dense<2, 20>(P, B, H, g, contact, list.data(), count, u, status, order_mode);
+    run_dense<1, 20>(P, B, H, g, contact, list.data(), count, u, status, order_mode);
+    return 0;
+  }
   run_dense<4, 10>(P, B, H, g, contact, list.data(), count, u, status, order_mode);
   run_dense<3, 10>(P, B, H, g, contact, list.data(), count, u, status, order_mode);
   run_dense<2, 10>(P, B, H, g, contact, list.data(), count, u, status, order_mode);

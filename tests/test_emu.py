@@ -87,12 +87,13 @@ def test_config4_schedules_and_normals_on_emulator(E, a1, O, horizon, B):
     assert np.abs(f - fo).max() <= TOL_F
 
 
-def test_dense_solve_on_emulator(E, a1, O):
+@pytest.mark.parametrize("horizon", [10, 20])      # 20: the direct classes run as a team of warps (Geo::TW)
+def test_dense_solve_on_emulator(E, a1, O, horizon):
     B = 10
     st = a1.gen_states(B, 4, 91)
     st["contact"][:6] = [0b0001, 0b0111, 0b1111, 0b0110, 0b1000, 0]
-    cfg = a1.default_config(horizon=10)
-    ocfg = O.make_config()
+    cfg = a1.default_config(horizon=horizon)
+    ocfg = O.make_config(horizon=horizon)
     ob = obatch(O, st)
     Hg = [O.build_qp(ocfg, ob, b) for b in range(B)]
     H = np.stack([x[0] for x in Hg]); g = np.stack([x[1] for x in Hg])
@@ -101,6 +102,8 @@ def test_dense_solve_on_emulator(E, a1, O):
         if st["contact"][b] == 0:
             assert status[b] == a1.STATUS_NO_CONTACT and np.abs(u[b]).max() == 0
             continue
+        if horizon == 20 and bin(int(st["contact"][b])).count("1") >= 3:
+            continue       # the library reports these as unsupported at N = 20 (dense H + factor exceed shared memory); not emulated
         uo, info = O.solve_dense(ocfg, H[b], g[b], st["contact"][b], O.MODE_EXACT)
         assert status[b] == 0 and np.abs(u[b] - uo).max() <= TOL_F, (b, status[b])
 
