@@ -190,7 +190,7 @@ int peer_signal(a1mpc_handle* h, int B) {
 int enqueue_solve(a1mpc_handle* h, int B, const DevInputs& din, const DevOutputs& dout_in, uint32_t* warm = nullptr, int shift = 0) {
   DevOutputs dout = dout_in;
   attach_peers(h, B, dout);
-  CK(cudaMemsetAsync(h->d_count, 0, 8 * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->d_count, 0, 16 * sizeof(int), h->stream));
   pack_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(din, B, h->d_rec, (int)h->cap, h->d_count, dout, h->cfg.horizon);
   h->launches++;
   CK(cudaEventRecord(h->ev_fork, h->stream));
@@ -299,7 +299,7 @@ int a1mpc_create(a1mpc_handle** out, const a1mpc_config* cfg, int device) {
     if (cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) != cudaSuccess) return bail(fail(A1MPC_ECUDA, "event create failed"));
   }
   if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(fail(A1MPC_ECUDA, "event create failed"));
-  if (cudaMalloc(&h->d_count, 8 * sizeof(int)) != cudaSuccess) return bail(fail(A1MPC_ENOMEM, "cudaMalloc failed"));
+  if (cudaMalloc(&h->d_count, 16 * sizeof(int)) != cudaSuccess) return bail(fail(A1MPC_ENOMEM, "cudaMalloc failed"));
   {
     cudaError_t e = (cfg->horizon == 10) ? fused_setup_n10(h->sm_count, h->cls) : fused_setup_n20(h->sm_count, h->cls);
     if (e != cudaSuccess) return bail(fail(A1MPC_ECUDA, std::string("kernel setup: ") + cudaGetErrorString(e)));
@@ -470,7 +470,7 @@ int a1mpc_solve_batch_ext(a1mpc_handle* h, int B, const a1mpc_inputs* in, const 
     dout = DevOutputs{h->d_f, h->d_status, out->iters ? h->d_iters : nullptr, out->u_full ? h->d_u : nullptr, Bs, f32};
   }
   attach_peers(h, -1, dout);   // the fused collect is wired to a1mpc_solve_batch / _warm only
-  CK(cudaMemsetAsync(h->d_count, 0, 8 * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->d_count, 0, 16 * sizeof(int), h->stream));
   if (h->ext_compact && dsched) {
     pack_ext2_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(di, dsched, dnorm, B, h->d_rec_ext, (int)h->cap_ext, h->d_count, dout, N);
     ext_launch(N, h->cls_ext, h->stream, B, h->P, h->d_rec_ext, h->d_count, dout);

@@ -149,9 +149,10 @@ __global__ void __launch_bounds__(32 * WPC) solve_kernel_sched2(const __grid_con
   // 0.43 instead of 0.25 ms at B = 1024, while the 4-stance kernel itself did not get faster -- its time is the slowest QP's
   // factorisation count times a per-factorisation latency that one warp per scheduler already has to itself.)
   const int gw = blockIdx.x * WPC + wib, nw = gridDim.x * WPC;
+  int* const head = const_cast<int*>(count) + 8 + 6;   // queue counter of this class (next_qp)
   uint32_t parity = 0;
 #pragma unroll 1
-  for (int q = gw; q < nq; q += nw) {
+  for (int q = gw; q < nq; q = next_qp(c, head, q, nw)) {
     if (lane == 0) tma_load_record(c.rec, rec + (size_t)q * REC_EXT_DOUBLES, c.bar, REC_EXT_DOUBLES * 8);
     mbar_wait(c.bar, parity);
     parity ^= 1u;

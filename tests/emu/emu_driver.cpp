@@ -116,7 +116,7 @@ int emu_solve_dense(const a1mpc_config* cfg, int B, const double* H, const doubl
   if (cfg->horizon != 10 && cfg->horizon != 20) return -1;
   const DevParams P = make_params(cfg);
   std::vector<int> list((size_t)4 * B + 8, 0);
-  int count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int count[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [0..7] class counts, [8..15] queue counters (next_qp)
   classify(B, contact, list.data(), count, u, 12 * cfg->horizon, status);
   if (cfg->horizon == 20) {   // a1mpc_dense.cu serves the direct classes at N = 20 (one or two stance feet)
     run_dense<2, 20>(P, B, H, g, contact, list.data(), count, u, status, order_mode);
@@ -137,7 +137,7 @@ int emu_grf_qp(int B, const double* root_acc, const double* rot_z, const double*
   std::memset(&P, 0, sizeof(P));
   P.N = 1; P.max_iter = 40; P.mu = 0.7; P.fzmax = 180.0; P.mu_switch = 1e-9;
   std::vector<int> list((size_t)4 * B + 8, 0);
-  int count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int count[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [0..7] class counts, [8..15] queue counters (next_qp)
   classify(B, contact, list.data(), count, f_body, 12, status);
   run_grf<4>(P, B, root_acc, rot_z, rot, foot, contact, list.data(), count, f_body, status, order_mode);
   run_grf<3>(P, B, root_acc, rot_z, rot, foot, contact, list.data(), count, f_body, status, order_mode);
@@ -156,7 +156,7 @@ int emu_solve_sched2(const a1mpc_config* cfg, int B, const a1mpc_inputs* in, con
   const DevParams P = make_params(cfg);
   const DevInputs din{in->x0, in->rot, in->foot, in->ref, in->contact, in->ld};
   const DevOutputs dout{o->f_body, o->status, o->iters, o->u_full, o->ld};
-  int count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int count[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [0..7] class counts, [8..15] queue counters (next_qp)
   std::vector<double> rec((size_t)B * REC_EXT_DOUBLES + 2);
   const int pb = 128, pgrid = (B + pb - 1) / pb;
   for (int bx = 0; bx < pgrid; ++bx)
@@ -227,7 +227,7 @@ int emu_solve_batch(const a1mpc_config* cfg, int B, const a1mpc_inputs* in, cons
   const DevInputs din{in->x0, in->rot, in->foot, in->ref, in->contact, in->ld};
   const DevOutputs dout{o->f_body, o->status, o->iters, o->u_full, o->ld};
   const size_t cap = (size_t)B;
-  int count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int count[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [0..7] class counts, [8..15] queue counters (next_qp)
   Stats st;
   const bool ext = sched || normals;
   std::vector<double> rec(cap * (ext ? (size_t)REC_EXT_DOUBLES : 4 * (size_t)REC_DOUBLES) + 2);
