@@ -13,4 +13,6 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:solv
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02z_launches_bench.csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-subrecords --ring 8 > $O/r02z_launches_bench.log 2>&1
 echo "== sanitizer"
 for t in memcheck racecheck synccheck; do timeout 400 compute-sanitizer --tool $t python __graft_entry__.py smoke > $O/r02z_sanitizer_$t.txt 2>&1; tail -3 $O/r02z_sanitizer_$t.txt; done
+# the team kernels and the queue with more QPs than slots: benchmark mix, N = 10 (B = 600) and N = 20 (B = 96)
+for t in memcheck racecheck synccheck; do for n in 10 20; do b=$([ $n = 10 ] && echo 600 || echo 96); echo "== $t prof_target2.py $n $b" >> $O/r02z_sanitizer_mix.txt; timeout 600 compute-sanitizer --tool $t python tools/prof_target2.py $n $b 2>&1 | tail -2 >> $O/r02z_sanitizer_mix.txt; done; done; cat $O/r02z_sanitizer_mix.txt
 echo "== robust sweep"; timeout 900 python tools/robust_sweep.py 2>&1 | tail -12 | tee $O/r02z_robust.txt

@@ -10,3 +10,6 @@ END { for (k in m) printf "%6d DMMA %2d UBLKCP %3d SYNCS %6d DFMA %3d MUFU.RSQ64
 echo
 echo "# excerpt: first lines with each mnemonic in solve_kernel<2,10,8,0,0> (the trot class)"
 cuobjdump -sass -fun 2>/dev/null '_ZN5a1mpc12solve_kernelILi2ELi10ELi8ELi0ELb0EEEvNS_9DevParamsEPKdPKiNS_10DevOutputsE' "$LIB" | grep -E "UBLKCP|SYNCS|DMMA|MUFU.RSQ64H" | awk '{k=$0; sub(/^[ \t]*\/\*[0-9a-f]+\*\/[ \t]*/,"",k); split(k,a," "); m=a[1]; if (m ~ /^@/) m=a[2]; sub(/\..*/,"",m); if (c[m]++ < 3) print "   " k}' | cut -c1-150
+echo
+echo "# warp teams: named-barrier instructions of solve_kernel<4,10,4,1,0> (four-stance class, two warps per QP): BAR.SYNC / BAR.RED with a barrier id register and 0x40 threads; ATOMG = the QP queue"
+cuobjdump -sass -fun 2>/dev/null '_ZN5a1mpc12solve_kernelILi4ELi10ELi4ELi1ELb0EEEvNS_9DevParamsEPKdPKiNS_10DevOutputsE' "$LIB" | grep -E "BAR\.|ATOMG|RED\.E" | awk '{k=$0; sub(/^[ \t]*\/\*[0-9a-f]+\*\/[ \t]*/,"",k); split(k,a," "); m=a[1]; if (m ~ /^@/) m=a[2]; n[m]++; if (c[m]++ < 2) print "   " k} END { for (m in n) printf "   # %d x %s\n", n[m], m }' | cut -c1-150
